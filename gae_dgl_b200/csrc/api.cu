@@ -1,0 +1,48 @@
+// Library-level entry points: version, per-thread error string, tuning knobs, launch counter.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gae {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+// defaults: LDG warp-per-row, 8 gathers in flight, 256 threads, plain caching, 1 row per warp
+static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {8}, {256}, {0}, {1}, {0}};
+static const char *const g_tuning_names[T_COUNT] = {"spmm_variant", "spmm_unroll", "spmm_block",
+                                                     "spmm_cache", "spmm_rows_per_warp", "dec_splits"};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int32_t tuning(int idx) { return g_tuning[idx].load(std::memory_order_relaxed); }
+
+}  // namespace gae
+
+extern "C" const char *gae_version(void) { return "gae_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *gae_last_error_string(void) { return gae::g_err; }
+extern "C" int64_t gae_launch_count(void) { return gae::g_launches.load(); }
+
+extern "C" int gae_set_tuning(const char *key, int32_t value) {
+    if (key) {
+        for (int i = 0; i < gae::T_COUNT; ++i)
+            if (strcmp(key, gae::g_tuning_names[i]) == 0) {
+                gae::g_tuning[i].store(value);
+                return GAE_OK;
+            }
+    }
+    gae::set_error("unknown tuning key '%s'", key ? key : "(null)");
+    return GAE_ERR_INVALID_ARG;
+}
+extern "C" int32_t gae_get_tuning(const char *key) {
+    if (key)
+        for (int i = 0; i < gae::T_COUNT; ++i)
+            if (strcmp(key, gae::g_tuning_names[i]) == 0) return gae::g_tuning[i].load();
+    return -1;
+}

@@ -1,0 +1,113 @@
+// Shared helpers for libgae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gae_b200.h"
+
+namespace gae {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int32_t tuning(int idx);
+
+enum TuningIdx {
+    T_SPMM_VARIANT = 0,  // 0 = LDG warp-per-row, 1 = bulk-async (cp.async.bulk) staged rows
+    T_SPMM_UNROLL,       // gathers in flight per lane group (4 / 8 / 16)
+    T_SPMM_BLOCK,        // threads per CTA (128 / 256 / 512)
+    T_SPMM_CACHE,        // 0 = plain ld.global.nc ; 1 = X evict_last + streaming idx/Y
+    T_SPMM_ROWS_PER_WARP,// 1 = warp per row, 2 = half-warp per row (d <= 64)
+    T_DEC_SPLITS,        // 0 = auto
+    T_COUNT
+};
+
+#define GAE_CHECK_ARG(cond, msg)                         \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            gae::set_error("invalid argument: %s", msg); \
+            return GAE_ERR_INVALID_ARG;                  \
+        }                                                \
+    } while (0)
+
+#define GAE_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            gae::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                    \
+            return (int)_e;                                                              \
+        }                                                                                \
+    } while (0)
+
+#define GAE_LAUNCH_CHECK()                                                               \
+    do {                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            gae::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                           __FILE__, __LINE__);                                          \
+            return (int)_e;                                                              \
+        }                                                                                \
+        gae::count_launch();                                                             \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_add(float4 &a, const float4 &b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+__device__ __forceinline__ void f4_fma(float4 &a, float w, const float4 &b) {
+    a.x = fmaf(w, b.x, a.x); a.y = fmaf(w, b.y, a.y); a.z = fmaf(w, b.z, a.z); a.w = fmaf(w, b.w, a.w);
+}
+__device__ __forceinline__ float4 f4_shfl_xor(const float4 &v, int m) {
+    float4 r;
+    r.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+    r.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    r.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+    r.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return r;
+}
+
+// 128-bit read-only gather of a feature row slice.
+__device__ __forceinline__ float4 ldg_f4(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+// Same, keeping the line resident in L2 (hub source rows are re-read by many dst rows).
+__device__ __forceinline__ float4 ldg_f4_evict_last(const float *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// Streaming (read-once) index load: do not pollute L1, evict first from L2.
+__device__ __forceinline__ int ld_stream_i32(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_f4(float *p, const float4 &v) {
+    __stcs(reinterpret_cast<float4 *>(p), v);
+}
+
+// Numerically stable pieces of BCE-with-logits, shared by decoder kernels.
+//   e = exp(-|x|);  l = log(1+e);  softplus(x) = max(x,0) + l;  softplus(-x) = max(-x,0) + l;
+//   sigmoid(x) = x>=0 ? 1/(1+e) : e/(1+e)
+__device__ __forceinline__ void softplus_parts(float x, float &l, float &sg) {
+    const float e = __expf(-fabsf(x));
+    const float one_e = 1.0f + e;
+    const float r = __frcp_rn(one_e);
+    l = __logf(one_e);
+    sg = (x >= 0.f) ? r : e * r;
+}
+
+}  // namespace gae

@@ -1,0 +1,379 @@
+// K5 / K6 -- fused InnerProductDecoder + weighted BCE-with-logits and its adjoint.
+//
+// Reference: logits = mm(zd, zd.t()) (gae.py:71), adj = g.adjacency_matrix().to_dense()
+// (train_inductive.py:44), loss = BCEWithLogits(logits, adj, pos_weight) (:48), backward
+// (:51).  The reference materialises three N x N fp32 arrays per step (adj, logits, grad);
+// here nothing N x N ever exists.  With y_ij = multiplicity of edge (j -> i):
+//     N^2 L = sum_ij softplus(x_ij) + sum_{e=(i,j)} [pw softplus(-x_ij) - softplus(x_ij)]
+//     dL/dx_ij = [ sigmoid(x_ij) - y_ij (pw (1 - sigmoid(x_ij)) + sigmoid(x_ij)) ] / N^2
+//     dL/dZd   = (G + G^T) Zd
+// The dense term is an attention-shaped pass: thread t owns R query rows z_i in registers,
+// streams key rows z_j from shared memory (warp-broadcast LDS.128), and keeps the running
+// loss and the d-wide gradient accumulator in registers -- one pass yields both the loss and
+// the gradient (FP32 FFMA + MUFU bound: 2d FFMA + ex2 + lg2 + rcp per pair).  The j range
+// is split across CTAs; split partials are combined in fixed order by the finalize kernel,
+// which also adds the per-edge correction from CSR and CSR(A^T).  No atomics: deterministic.
+#include "common.cuh"
+
+namespace gae {
+
+constexpr int DEC_THREADS = 128;
+
+struct DecConfig {
+    int D;             // padded embedding width (16 / 32 / 64)
+    int R;             // query rows per thread
+    int JT;            // key rows per shared-memory tile
+    int64_t nb;        // query row blocks
+    int splits;        // key range splits
+    int64_t j_chunk;   // key rows per split
+    int64_t fin_blocks;
+};
+
+static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
+    if (d <= 16) { c->D = 16; c->R = 2; }
+    else if (d <= 32) { c->D = 32; c->R = 1; }
+    else if (d <= 64) { c->D = 64; c->R = 1; }
+    else return false;
+    c->JT = 2048 / c->D;
+    const int64_t rows_per_block = (int64_t)DEC_THREADS * c->R;
+    c->nb = cdiv(n, rows_per_block);
+    int64_t want = tuning(T_DEC_SPLITS);
+    if (want <= 0) want = cdiv(148 * 6, c->nb);
+    int64_t max_splits = cdiv(n, c->JT);
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    c->j_chunk = cdiv(cdiv(n, want), c->JT) * c->JT;
+    c->splits = (int)cdiv(n, c->j_chunk);
+    const int rows_per_fin_block = 256 / (c->D / 4);
+    c->fin_blocks = cdiv(n, rows_per_fin_block);
+    return true;
+}
+
+template <int D, int R, bool LOSS, bool GRAD>
+__global__ void __launch_bounds__(DEC_THREADS)
+dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
+                 float *__restrict__ dz_part, double *__restrict__ loss_part) {
+    constexpr int JT = 2048 / D;
+    __shared__ __align__(16) float Zs[JT][D];
+    __shared__ double red[DEC_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * DEC_THREADS * R;
+    const int64_t jbeg = (int64_t)blockIdx.y * j_chunk;
+    const int64_t jend = min(n, jbeg + j_chunk);
+
+    float zi[R][D];
+    float acc[R][D];
+    float lsum[R];
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t i = i0 + (int64_t)r * DEC_THREADS + tid;
+        valid[r] = i < n;
+        lsum[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            zi[r][k] = (valid[r] && k < d) ? __ldg(Zd + i * ldz + k) : 0.f;
+            acc[r][k] = 0.f;
+        }
+    }
+
+    for (int64_t j0 = jbeg; j0 < jend; j0 += JT) {
+        const int jcount = (int)min((int64_t)JT, jend - j0);
+        __syncthreads();
+        for (int t = tid; t < JT * D; t += DEC_THREADS) {
+            const int jj = t / D, k = t % D;
+            Zs[jj][k] = (jj < jcount && k < d) ? __ldg(Zd + (j0 + jj) * ldz + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int jj = 0; jj < jcount; ++jj) {
+            float zj[D];
+#pragma unroll
+            for (int k4 = 0; k4 < D / 4; ++k4) {
+                const float4 q = *reinterpret_cast<const float4 *>(&Zs[jj][k4 * 4]);
+                zj[k4 * 4 + 0] = q.x; zj[k4 * 4 + 1] = q.y; zj[k4 * 4 + 2] = q.z; zj[k4 * 4 + 3] = q.w;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float x = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) x = fmaf(zi[r][k], zj[k], x);
+                float l, sg;
+                softplus_parts(x, l, sg);
+                if (LOSS) lsum[r] += fmaxf(x, 0.f) + l;
+                if (GRAD) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc[r][k] = fmaf(sg, zj[k], acc[r][k]);
+                }
+            }
+        }
+    }
+
+    if (GRAD) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t i = i0 + (int64_t)r * DEC_THREADS + tid;
+            if (!valid[r]) continue;
+            float4 *o = reinterpret_cast<float4 *>(dz_part + ((int64_t)blockIdx.y * n + i) * D);
+#pragma unroll
+            for (int k4 = 0; k4 < D / 4; ++k4)
+                o[k4] = make_float4(acc[r][k4 * 4], acc[r][k4 * 4 + 1], acc[r][k4 * 4 + 2], acc[r][k4 * 4 + 3]);
+        }
+    }
+    if (LOSS) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += valid[r] ? (double)lsum[r] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < DEC_THREADS / 32; ++w) t += red[w];
+            loss_part[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// One lane group (D/4 lanes) per row: ordered split reduce + per-edge corrections.
+template <int D>
+__global__ void __launch_bounds__(256)
+dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
+                    const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                    const int64_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t, float pw,
+                    const float *__restrict__ dz_part, int splits, int mode, float inv_n2,
+                    float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part) {
+    constexpr int LPR = D / 4;
+    constexpr int RPB = 256 / LPR;
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const int sub = tid % LPR;
+    const int64_t i = (int64_t)blockIdx.x * RPB + tid / LPR;
+    const bool valid = i < n;
+    const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
+
+    auto load_row = [&](int64_t r) -> float4 {
+        float4 v = f4_zero();
+        const float *p = Zd + r * ldz + sub * 4;
+        if (sub * 4 + 0 < d) v.x = __ldg(p + 0);
+        if (sub * 4 + 1 < d) v.y = __ldg(p + 1);
+        if (sub * 4 + 2 < d) v.z = __ldg(p + 2);
+        if (sub * 4 + 3 < d) v.w = __ldg(p + 3);
+        return v;
+    };
+    auto group_dot = [&](const float4 &a, const float4 &b) -> float {
+        float x = a.x * b.x;
+        x = fmaf(a.y, b.y, x); x = fmaf(a.z, b.z, x); x = fmaf(a.w, b.w, x);
+#pragma unroll
+        for (int off = 1; off < LPR; off <<= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        return x;
+    };
+
+    const float4 zi = valid ? load_row(i) : f4_zero();
+    float4 g = f4_zero();
+    if (want_grad && valid) {
+        for (int s = 0; s < splits; ++s)
+            f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
+        // x_ij = x_ji: (G + G^T) Zd doubles the dense term
+        g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
+    }
+    float lsum = 0.f;
+    // groups of one warp walk different rows: loop to the warp-wide max degree so the
+    // shuffles inside group_dot stay convergent
+    {
+        const int64_t e0 = valid ? rowptr[i] : 0, e1 = valid ? rowptr[i + 1] : 0;
+        int64_t len = e1 - e0, maxlen = len;
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
+        for (int64_t t = 0; t < maxlen; ++t) {
+            const bool on = t < len;
+            const float4 zj = on ? load_row(col[e0 + t]) : f4_zero();
+            const float x = group_dot(zi, zj);
+            float l, sg;
+            softplus_parts(x, l, sg);
+            if (on) {
+                lsum += pw * (fmaxf(-x, 0.f) + l) - (fmaxf(x, 0.f) + l);
+                const float c = -(pw * (1.f - sg) + sg);
+                f4_fma(g, c, zj);
+            }
+        }
+    }
+    if (want_grad) {
+        const int64_t e0 = valid ? rowptr_t[i] : 0, e1 = valid ? rowptr_t[i + 1] : 0;
+        int64_t len = e1 - e0, maxlen = len;
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
+        for (int64_t t = 0; t < maxlen; ++t) {
+            const bool on = t < len;
+            const float4 zj = on ? load_row(col_t[e0 + t]) : f4_zero();
+            const float x = group_dot(zi, zj);
+            float l, sg;
+            softplus_parts(x, l, sg);
+            if (on) {
+                const float c = -(pw * (1.f - sg) + sg);
+                f4_fma(g, c, zj);
+            }
+        }
+        if (valid) {
+            float *o = dZ + i * ld_dz + sub * 4;
+            if (sub * 4 + 0 < d) o[0] = g.x * inv_n2;
+            if (sub * 4 + 1 < d) o[1] = g.y * inv_n2;
+            if (sub * 4 + 2 < d) o[2] = g.z * inv_n2;
+            if (sub * 4 + 3 < d) o[3] = g.w * inv_n2;
+        }
+    }
+    if (want_loss) {
+        double s = (valid && sub == 0) ? (double)lsum : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            loss_part[blockIdx.x] = t;
+        }
+    }
+}
+
+// loss = (sum dense partials + sum edge partials) / N^2, fixed order, fp64 accumulate
+__global__ void dec_loss_reduce_kernel(const double *__restrict__ part, int64_t count, double inv_n2,
+                                       float *__restrict__ loss) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < count; i += 256) s += part[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = (float)(red[0] * inv_n2);
+}
+
+// Materialised logits X = Zd Zd^T (compatibility path: GAE.forward returns [N,N]).
+__global__ void __launch_bounds__(256)
+dec_logits_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, float *__restrict__ X, int64_t ldx) {
+    constexpr int T = 64, KC = 16;
+    __shared__ float Zi[KC][T + 1], Zj[KC][T + 1];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int64_t i0 = (int64_t)blockIdx.y * T, j0 = (int64_t)blockIdx.x * T;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < d; k0 += KC) {
+        __syncthreads();
+        for (int t = tid; t < T * KC; t += 256) {
+            const int r = t / KC, k = t % KC;
+            Zi[k][r] = (i0 + r < n && k0 + k < d) ? __ldg(Zd + (i0 + r) * ldz + k0 + k) : 0.f;
+            Zj[k][r] = (j0 + r < n && k0 + k < d) ? __ldg(Zd + (j0 + r) * ldz + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = Zi[k][ty * 4 + q]; b[q] = Zj[k][tx + 16 * q]; }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int64_t i = i0 + ty * 4 + p;
+        if (i >= n) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t j = j0 + tx + 16 * q;
+            if (j < n) X[i * ldx + j] = acc[p][q];
+        }
+    }
+}
+
+template <int D, int R>
+static cudaError_t launch_dense(const DecConfig &c, int mode, const float *Zd, int64_t ldz, int64_t n, int d,
+                                float *dz_part, double *loss_part, cudaStream_t st) {
+    dim3 grid((unsigned)c.nb, (unsigned)c.splits);
+    const bool L = mode & GAE_DEC_LOSS, G = mode & GAE_DEC_GRAD;
+    if (L && G) dec_dense_kernel<D, R, true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
+    else if (L) dec_dense_kernel<D, R, true, false><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
+    else dec_dense_kernel<D, R, false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace gae
+
+using namespace gae;
+
+static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int64_t gae_decoder_ws_bytes(int64_t n, int32_t d) {
+    DecConfig c;
+    if (n <= 0 || d <= 0 || !dec_config(n, d, &c)) return 0;
+    const int64_t dz = align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256);
+    const int64_t lp = (int64_t)sizeof(double) * (c.nb * c.splits + c.fin_blocks);
+    return dz + align_up(lp, 256);
+}
+
+extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d,
+                                   const int64_t *rowptr, const int32_t *col, const int64_t *rowptr_t,
+                                   const int32_t *col_t, float pos_weight, int32_t mode, float *loss,
+                                   float *dZd_unit, int64_t ld_dz, void *ws, int64_t ws_bytes, void *stream) {
+    GAE_CHECK_ARG(n > 0 && d > 0, "n, d must be > 0");
+    GAE_CHECK_ARG(Zd && rowptr, "null pointer");
+    GAE_CHECK_ARG(ldz >= d, "ldz too small");
+    GAE_CHECK_ARG((mode & ~3) == 0 && mode != 0, "mode must be a combination of GAE_DEC_LOSS|GAE_DEC_GRAD");
+    const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
+    GAE_CHECK_ARG(!want_loss || loss, "loss pointer required");
+    GAE_CHECK_ARG(!want_grad || (dZd_unit && rowptr_t && ld_dz >= d), "gradient needs dZd_unit and CSR(A^T)");
+    DecConfig c;
+    if (!dec_config(n, d, &c)) {
+        set_error("decoder supports embedding width d <= 64 (got %d)", d);
+        return GAE_ERR_UNSUPPORTED;
+    }
+    if (!ws || ws_bytes < gae_decoder_ws_bytes(n, d)) {
+        set_error("decoder workspace too small: have %lld need %lld", (long long)ws_bytes,
+                  (long long)gae_decoder_ws_bytes(n, d));
+        return GAE_ERR_WORKSPACE;
+    }
+    GAE_CHECK_ARG(aligned16(ws), "workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *dz_part = (float *)ws;
+    double *loss_part = (double *)((char *)ws + align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256));
+    double *loss_part_edges = loss_part + c.nb * c.splits;
+
+    if (c.D == 16) GAE_CUDA((launch_dense<16, 2>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
+    else if (c.D == 32) GAE_CUDA((launch_dense<32, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
+    else GAE_CUDA((launch_dense<64, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
+
+    const float inv_n2 = (float)(1.0 / ((double)n * (double)n));
+    if (c.D == 16)
+        dec_finalize_kernel<16><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+    else if (c.D == 32)
+        dec_finalize_kernel<32><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+    else
+        dec_finalize_kernel<64><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+    GAE_LAUNCH_CHECK();
+    if (want_loss) {
+        dec_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, c.nb * c.splits + c.fin_blocks,
+                                                  1.0 / ((double)n * (double)n), loss);
+        GAE_LAUNCH_CHECK();
+    }
+    return GAE_OK;
+}
+
+extern "C" int gae_decoder_logits_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, float *X, int64_t ldx,
+                                      void *stream) {
+    GAE_CHECK_ARG(n >= 0 && d > 0, "bad sizes");
+    if (n == 0) return GAE_OK;
+    GAE_CHECK_ARG(Zd && X && ldz >= d && ldx >= n, "bad pointers / leading dimensions");
+    dim3 grid((unsigned)cdiv(n, 64), (unsigned)cdiv(n, 64));
+    dec_logits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Zd, ldz, n, d, X, ldx);
+    GAE_LAUNCH_CHECK();
+    return GAE_OK;
+}

@@ -1,0 +1,254 @@
+// K3 -- NodeApplyModule: H = act(Yin W^T + b) and its adjoint (reference gae.py:7-16).
+//
+// The dense products here are skinny (d_out = 32 / 16, K = d_in) fp32 GEMMs that must match
+// torch's fp32 nn.Linear to 1e-5, so they run as SIMT FFMA tiles (TF32 tensor cores would
+// break the tolerance; the work is <1 % of a step).  One strided,
+// shared-memory-tiled kernel serves the three products:
+//   fwd : H[n,do]    = Yin[n,di]   . W^T          (+ bias, activation)
+//   dY  : dYin[n,di] = dPre[n,do]  . W
+//   dW  : dW[do,di]  = dPre^T      . Yin           (split over n, ordered reduce)
+// with dPre = dH * (H > 0) applied on the fly when the layer has a ReLU.
+#include "common.cuh"
+
+namespace gae {
+
+struct GemmArgs {
+    const float *A; int64_t a_rs, a_cs;      // A(m,k) = A[m*a_rs + k*a_cs]
+    const float *Mask; int64_t m_rs, m_cs;   // optional: A(m,k) *= (Mask(m,k) > 0)
+    const float *B; int64_t b_rs, b_cs;      // B(k,n) = B[k*b_rs + n*b_cs]
+    float *C; int64_t ldc;                   // C[m*ldc + n] ; split z adds z*c_split_stride
+    int64_t c_split_stride;
+    const float *bias;                       // optional [N]
+    int64_t M, N, K;
+    int64_t k_chunk;                         // K range per blockIdx.z
+    int act;
+};
+
+constexpr int BM = 64, BK = 16, GEMM_THREADS = 128;
+
+template <int BN, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmArgs g) {
+    constexpr int TM = 4, TN = BN / 8;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid / 8, tx = tid % 8;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int64_t n0 = (int64_t)blockIdx.y * BN;
+    const int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
+    const int64_t kend = min(g.K, kbeg + g.k_chunk);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        // stage A tile [BM x BK]
+        for (int i = tid; i < BM * BK; i += GEMM_THREADS) {
+            int mm, kk;
+            if (A_KC) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
+            const int64_t m = m0 + mm, k = k0 + kk;
+            float v = 0.f;
+            if (m < g.M && k < kend) {
+                v = __ldg(g.A + m * g.a_rs + k * g.a_cs);
+                if (g.Mask && !(__ldg(g.Mask + m * g.m_rs + k * g.m_cs) > 0.f)) v = 0.f;
+            }
+            As[kk][mm] = v;
+        }
+        for (int i = tid; i < BN * BK; i += GEMM_THREADS) {
+            int nn, kk;
+            if (B_KC) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
+            const int64_t n = n0 + nn, k = k0 + kk;
+            Bs[kk][nn] = (n < g.N && k < kend) ? __ldg(g.B + k * g.b_rs + n * g.b_cs) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *C = g.C + (int64_t)blockIdx.z * g.c_split_stride;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int64_t n = n0 + tx * TN + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (g.bias) v += __ldg(g.bias + n);
+            if (g.act == GAE_ACT_RELU) v = fmaxf(v, 0.f);
+            C[m * g.ldc + n] = v;
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+static cudaError_t launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
+    if (g.M == 0 || g.N == 0) return cudaSuccess;
+    if (g.N <= 16) {
+        dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 16), splits);
+        sgemm_kernel<16, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+    } else if (g.N <= 32) {
+        dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 32), splits);
+        sgemm_kernel<32, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+    } else {
+        dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 64), splits);
+        sgemm_kernel<64, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// out[i] = sum_z part[z*stride + i] in fixed z order (deterministic split-K reduce)
+__global__ void split_reduce_kernel(const float *__restrict__ part, int64_t stride, int splits,
+                                    float *__restrict__ out, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
+    out[i] = s;
+}
+
+// partial column sums of dPre = dH * (H > 0): part[z, j] over row chunk z
+__global__ void colsum_masked_kernel(const float *__restrict__ dH, int64_t ld_dh,
+                                     const float *__restrict__ H, int64_t ld_h, int relu, int64_t n,
+                                     int d_out, int64_t rows_per_block, float *__restrict__ part) {
+    // blockDim = (32, 8): x over columns, y over rows
+    __shared__ float red[8][33];
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(n, r0 + rows_per_block);
+    for (int j0 = 0; j0 < d_out; j0 += 32) {
+        const int j = j0 + threadIdx.x;
+        float s = 0.f;
+        if (j < d_out)
+            for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+                float v = dH[r * ld_dh + j];
+                if (relu && !(H[r * ld_h + j] > 0.f)) v = 0.f;
+                s += v;
+            }
+        red[threadIdx.y][threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.y == 0 && j < d_out) {
+            float t = 0.f;
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+            part[(int64_t)blockIdx.x * d_out + j] = t;
+        }
+        __syncthreads();
+    }
+}
+
+static void bwd_split_config(int64_t n, int32_t d_in, int32_t d_out, int *splits, int64_t *k_chunk) {
+    // enough CTAs to fill 148 SMs a few times, chunks a multiple of BK, at most 1024 splits
+    const int64_t tiles = cdiv(d_out, BM) * cdiv(d_in, 64);
+    int64_t want = cdiv(148 * 4, tiles);
+    int64_t chunk = cdiv(cdiv(n, want), BK) * BK;
+    if (chunk < 256) chunk = 256;
+    int64_t s = cdiv(n, chunk);
+    if (s > 1024) { chunk = cdiv(cdiv(n, 1024), BK) * BK; s = cdiv(n, chunk); }
+    if (s < 1) s = 1;
+    *splits = (int)s;
+    *k_chunk = chunk;
+}
+
+}  // namespace gae
+
+using namespace gae;
+
+extern "C" int gae_linear_fwd_f32(const float *Yin, int64_t ld_in, const float *W, const float *b,
+                                  float *H, int64_t ld_out, int64_t n, int32_t d_in, int32_t d_out,
+                                  int32_t act, void *stream) {
+    GAE_CHECK_ARG(n >= 0 && d_in > 0 && d_out > 0, "bad sizes");
+    if (n == 0) return GAE_OK;
+    GAE_CHECK_ARG(Yin && W && H, "null pointer");
+    GAE_CHECK_ARG(ld_in >= d_in && ld_out >= d_out, "leading dimension too small");
+    GAE_CHECK_ARG(act == GAE_ACT_IDENTITY || act == GAE_ACT_RELU, "unknown activation");
+    GemmArgs g{};
+    g.A = Yin; g.a_rs = ld_in; g.a_cs = 1;
+    g.B = W; g.b_rs = 1; g.b_cs = d_in;   // B(k, j) = W[j, k]
+    g.C = H; g.ldc = ld_out; g.bias = b;
+    g.M = n; g.N = d_out; g.K = d_in; g.k_chunk = d_in; g.act = act;
+    GAE_CUDA((launch_gemm<true, true>(g, 1, (cudaStream_t)stream)));
+    return GAE_OK;
+}
+
+extern "C" int64_t gae_linear_bwd_ws_bytes(int64_t n, int32_t d_in, int32_t d_out) {
+    if (n <= 0 || d_in <= 0 || d_out <= 0) return 0;
+    int splits; int64_t chunk;
+    bwd_split_config(n, d_in, d_out, &splits, &chunk);
+    const int64_t db_blocks = cdiv(n, 2048);
+    return (int64_t)sizeof(float) * ((int64_t)splits * d_out * d_in + db_blocks * d_out);
+}
+
+extern "C" int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *W, const float *H,
+                                  int64_t ld_out, const float *dH, int64_t ld_dh, float *dYin,
+                                  int64_t ld_dyin, float *dW, float *db, void *ws, int64_t ws_bytes,
+                                  int64_t n, int32_t d_in, int32_t d_out, int32_t act, void *stream) {
+    GAE_CHECK_ARG(n >= 0 && d_in > 0 && d_out > 0, "bad sizes");
+    GAE_CHECK_ARG(Yin && W && dH && dW && db, "null pointer");
+    GAE_CHECK_ARG(act == GAE_ACT_IDENTITY || (act == GAE_ACT_RELU && H), "ReLU adjoint needs H");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        GAE_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)d_out * d_in, st));
+        GAE_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)d_out, st));
+        return GAE_OK;
+    }
+    if (ws_bytes < gae_linear_bwd_ws_bytes(n, d_in, d_out) || !ws) {
+        set_error("linear_bwd workspace too small: have %lld need %lld", (long long)ws_bytes,
+                  (long long)gae_linear_bwd_ws_bytes(n, d_in, d_out));
+        return GAE_ERR_WORKSPACE;
+    }
+    const float *mask = (act == GAE_ACT_RELU) ? H : nullptr;
+    int splits; int64_t chunk;
+    bwd_split_config(n, d_in, d_out, &splits, &chunk);
+    float *part_w = (float *)ws;
+    float *part_b = part_w + (int64_t)splits * d_out * d_in;
+
+    // dW[j,k] = sum_n dPre[n,j] Yin[n,k]:  A(m=j,k=n) = dH[n*ld + j], B(k=n, n=k) = Yin[n*ld + k]
+    {
+        GemmArgs g{};
+        g.A = dH; g.a_rs = 1; g.a_cs = ld_dh;
+        g.Mask = mask; g.m_rs = 1; g.m_cs = ld_out;
+        g.B = Yin; g.b_rs = ld_in; g.b_cs = 1;
+        g.C = part_w; g.ldc = d_in; g.c_split_stride = (int64_t)d_out * d_in;
+        g.M = d_out; g.N = d_in; g.K = n; g.k_chunk = chunk; g.act = GAE_ACT_IDENTITY;
+        GAE_CUDA((launch_gemm<false, false>(g, splits, st)));
+        const int64_t cnt = (int64_t)d_out * d_in;
+        split_reduce_kernel<<<(unsigned)cdiv(cnt, 256), 256, 0, st>>>(part_w, cnt, splits, dW, cnt);
+        GAE_LAUNCH_CHECK();
+    }
+    // db[j] = sum_n dPre[n,j]
+    {
+        const int64_t rows_per_block = 2048;
+        const int64_t blocks = cdiv(n, rows_per_block);
+        colsum_masked_kernel<<<(unsigned)blocks, dim3(32, 8), 0, st>>>(dH, ld_dh, mask, ld_out, mask != nullptr, n,
+                                                                       d_out, rows_per_block, part_b);
+        GAE_LAUNCH_CHECK();
+        split_reduce_kernel<<<(unsigned)cdiv(d_out, 256), 256, 0, st>>>(part_b, d_out, (int)blocks, db, d_out);
+        GAE_LAUNCH_CHECK();
+    }
+    // dYin[n,k] = sum_j dPre[n,j] W[j,k]
+    if (dYin) {
+        GAE_CHECK_ARG(ld_dyin >= d_in, "ld_dyin too small");
+        GemmArgs g{};
+        g.A = dH; g.a_rs = ld_dh; g.a_cs = 1;
+        g.Mask = mask; g.m_rs = ld_out; g.m_cs = 1;
+        g.B = W; g.b_rs = d_in; g.b_cs = 1;
+        g.C = dYin; g.ldc = ld_dyin;
+        g.M = n; g.N = d_in; g.K = d_out; g.k_chunk = d_out; g.act = GAE_ACT_IDENTITY;
+        GAE_CUDA((launch_gemm<true, false>(g, 1, st)));
+    }
+    return GAE_OK;
+}

@@ -1,0 +1,209 @@
+"""Drop-in for /root/reference/gae_dgl/gae.py on the B200 kernels.
+
+Same classes, constructor signatures, attribute names and state_dict keys
+(`layers.{i}.apply_mod.linear.{weight,bias}`) as the reference, so checkpoints written by
+either load into the other.  Differences, all additive:
+  * `GAE.loss(g)` / `GAE.reconstruction_loss(g)`: the fused decoder + weighted BCE path that
+    never materialises N x N (what the trainers in this package call);
+  * `InnerProductDecoder.forward(z, mask=None)` accepts an injected keep-mask (parity tests);
+  * `VGAE` (not present in the reference, which only cites the paper, README.md:58).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .graph import DGLGraph, function as fn
+
+_IDENTITY = lambda x: x  # noqa: E731  (gae.py:43,45,47 use `lambda x:x`)
+
+
+def _act_code(activation) -> Optional[int]:
+    if activation in (F.relu, torch.relu):
+        return ops.ACT_RELU
+    if activation is _IDENTITY or activation is None:
+        return ops.ACT_IDENTITY
+    return None  # arbitrary callable: applied after an identity-fused linear
+
+
+class NodeApplyModule(nn.Module):
+    """gae.py:7-16 -- Linear + activation applied to the node frame."""
+
+    def __init__(self, in_feats, out_feats, activation):
+        super().__init__()
+        self.linear = nn.Linear(in_feats, out_feats)
+        self.activation = activation
+
+    def forward(self, node):
+        code = _act_code(self.activation)
+        h = ops.LinearActFunction.apply(node.data['h'], self.linear.weight, self.linear.bias,
+                                        ops.ACT_IDENTITY if code is None else code)
+        if code is None:
+            h = self.activation(h)
+        return {'h': h}
+
+
+gcn_msg = fn.copy_src(src='h', out='m')      # gae.py:18
+gcn_reduce = fn.sum(msg='m', out='h')        # gae.py:19  (sum aggregation)
+
+
+class GCN(nn.Module):
+    """gae.py:21-31 -- aggregate first (SpMM), then NodeApplyModule."""
+
+    def __init__(self, in_feats, out_feats, activation):
+        super().__init__()
+        self.apply_mod = NodeApplyModule(in_feats, out_feats, activation)
+
+    def forward(self, g, feature):
+        g.ndata['h'] = feature
+        g.update_all(gcn_msg, gcn_reduce)
+        g.apply_nodes(func=self.apply_mod)
+        h = g.ndata.pop('h')
+        return h
+
+
+def _build_layers(in_dim: int, hidden_dims: Sequence[int]):
+    # gae.py:35-45: ReLU on every layer but the last; a single layer gets the identity
+    if len(hidden_dims) >= 2:
+        layers = [GCN(in_dim, hidden_dims[0], F.relu)]
+        for i in range(1, len(hidden_dims)):
+            if i != len(hidden_dims) - 1:
+                layers.append(GCN(hidden_dims[i - 1], hidden_dims[i], F.relu))
+            else:
+                layers.append(GCN(hidden_dims[i - 1], hidden_dims[i], _IDENTITY))
+    else:
+        layers = [GCN(in_dim, hidden_dims[0], _IDENTITY)]
+    return layers
+
+
+class InnerProductDecoder(nn.Module):
+    """gae.py:63-72.  Dropout is applied with training=True ALWAYS (F.dropout default), one
+    mask shared by both factors of z z^T."""
+
+    def __init__(self, activation=torch.sigmoid, dropout=0.1):
+        super().__init__()
+        self.dropout = dropout
+        self.activation = activation
+
+    @staticmethod
+    def _rng():
+        # seed/offset for the Philox mask come from torch's generator so torch.manual_seed
+        # controls them; two int64 draws on the host, no device sync
+        s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
+        return int(s[0]), int(s[1])
+
+    def forward(self, z, mask: Optional[torch.Tensor] = None):
+        seed, offset = (0, 0) if mask is not None else self._rng()
+        x = ops.DecoderLogitsFunction.apply(z, float(self.dropout), mask, seed, offset)
+        return self.activation(x)
+
+    def loss(self, z, g: DGLGraph, pos_weight: float, mask: Optional[torch.Tensor] = None):
+        """Fused path: mean BCE-with-logits(z_d z_d^T, A, pos_weight) without the N x N arrays
+        (replaces gae.py:71 + train_inductive.py:44,48)."""
+        seed, offset = (0, 0) if mask is not None else self._rng()
+        return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, seed, offset)
+
+
+def pos_weight_of(g: DGLGraph, transductive: bool = False) -> float:
+    """train_inductive.py:46 / train_transductive.py:60 evaluated from integers: the sum of the
+    dense adjacency equals the edge count (with multiplicity), exactly representable in fp32
+    below 2^24 edges; the arithmetic below repeats the reference's fp32 tensor ops."""
+    n = g.number_of_nodes()
+    adj_sum = torch.tensor(float(g.number_of_edges()), dtype=torch.float32)
+    if transductive:
+        return float(torch.Tensor([float(n * n - adj_sum) / adj_sum])[0])
+    return float((n * n - adj_sum) / adj_sum)
+
+
+class GAE(nn.Module):
+    """gae.py:33-61."""
+
+    def __init__(self, in_dim, hidden_dims):
+        super().__init__()
+        self.layers = nn.ModuleList(_build_layers(in_dim, hidden_dims))
+        self.decoder = InnerProductDecoder(activation=_IDENTITY)
+
+    def forward(self, g):
+        h = g.ndata['h']
+        for conv in self.layers:
+            h = conv(g, h)
+        g.ndata['h'] = h          # gae.py:53 side effect kept: features replaced by embeddings
+        adj_rec = self.decoder(h)
+        return adj_rec
+
+    def encode(self, g):
+        h = g.ndata['h']
+        for conv in self.layers:
+            h = conv(g, h)
+        return h
+
+    def loss(self, g, pos_weight: Optional[float] = None, mask: Optional[torch.Tensor] = None,
+             transductive: bool = False):
+        """Fused equivalent of `BCELoss(model.forward(g), adj, pos_weight)`
+        (train_inductive.py:44-48), including the gae.py:53 write-back."""
+        h = self.encode(g)
+        g.ndata['h'] = h
+        if pos_weight is None:
+            pos_weight = pos_weight_of(g, transductive)
+        return self.decoder.loss(h, g, pos_weight, mask)
+
+    reconstruction_loss = loss
+
+
+class VGAE(nn.Module):
+    """Variational GAE (Kipf & Welling 2016), same constructor as GAE.  Not in the reference
+    (README.md:58 cites the paper only): shared GCN trunk over hidden_dims[:-1], two GCN heads
+    (mu, log sigma) of width hidden_dims[-1], reparameterisation, inner-product decoder.
+    `loss(g)` returns reconstruction + KL."""
+
+    def __init__(self, in_dim, hidden_dims):
+        super().__init__()
+        hidden_dims = list(hidden_dims)
+        if len(hidden_dims) >= 2:
+            trunk = _build_layers(in_dim, hidden_dims[:-1] + [hidden_dims[-1]])[:-1]
+            head_in = hidden_dims[-2]
+        else:
+            trunk, head_in = [], in_dim
+        self.layers = nn.ModuleList(trunk)
+        self.mu_head = GCN(head_in, hidden_dims[-1], _IDENTITY)
+        self.logstd_head = GCN(head_in, hidden_dims[-1], _IDENTITY)
+        self.decoder = InnerProductDecoder(activation=_IDENTITY)
+
+    def encode_dist(self, g):
+        h = g.ndata['h']
+        for conv in self.layers:
+            h = conv(g, h)
+        return self.mu_head(g, h), self.logstd_head(g, h)
+
+    def encode(self, g):
+        return self.encode_dist(g)[0]
+
+    def _sample(self, mu, logstd, eps=None):
+        if not self.training and eps is None:
+            return mu
+        if eps is None:
+            eps = torch.randn_like(mu)
+        return mu + eps * torch.exp(logstd)
+
+    @staticmethod
+    def kl(mu, logstd):
+        n = mu.shape[0]
+        return -0.5 / n * torch.mean(torch.sum(1 + 2 * logstd - mu.pow(2) - torch.exp(2 * logstd), dim=1))
+
+    def forward(self, g, eps=None):
+        mu, logstd = self.encode_dist(g)
+        z = self._sample(mu, logstd, eps)
+        g.ndata['h'] = z
+        return self.decoder(z)
+
+    def loss(self, g, pos_weight: Optional[float] = None, mask=None, eps=None, transductive=False):
+        mu, logstd = self.encode_dist(g)
+        z = self._sample(mu, logstd, eps)
+        g.ndata['h'] = z
+        if pos_weight is None:
+            pos_weight = pos_weight_of(g, transductive)
+        return self.decoder.loss(z, g, pos_weight, mask) + self.kl(mu, logstd)

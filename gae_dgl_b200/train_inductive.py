@@ -1,0 +1,181 @@
+"""Drop-in for /root/reference/gae_dgl/train_inductive.py (ZINC-250k style batched training).
+
+Same flags (train_inductive.py:18-26), same Trainer.iteration / Trainer.save contract
+(:37-57), same per-epoch checkpoint name `ep{NN}.pkl` holding `model.state_dict()`.
+What changed underneath: the loss is the fused decoder + weighted-BCE kernel
+(`model.loss(bg)`), so the dense N x N adjacency / logits of :44-48 are never built; batches
+are collated straight into a device CSR.  `--dense_decoder` runs the reference's materialised
+formulation (forward -> dense adj -> torch BCE) for comparison.
+Reference defects repaired: `save_dir` NameError (:71), `plt.save` (:67), missing
+`--hidden_dims` default (:23).  `--synthetic N` generates N ZINC-shaped molecules when the
+pickled dataset is not available (it needs RDKit + a download, neither present here).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import torch
+from torch.nn.functional import binary_cross_entropy_with_logits as BCELoss
+from torch.utils.data import DataLoader
+
+from . import graph as dgl
+from .dataset import MolDataset
+from .gae import GAE, VGAE
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='Pre-train GAE')
+    parser.add_argument('--n_epochs', '-e', type=int, default=10, help='number of epochs')
+    parser.add_argument('--data_file', '-d', type=str, default='data/graphs.pkl', help='data file')
+    parser.add_argument('--save_dir', '-s', type=str, default='../result', help='result directry')
+    parser.add_argument('--in_dim', '-i', type=int, default=39, help='input dimension')
+    parser.add_argument('--hidden_dims', metavar='N', type=int, nargs='+', default=[32, 16],
+                        help='list of hidden dimensions')
+    parser.add_argument('--batch_size', '-b', type=int, default=128, help='batch size')
+    parser.add_argument('--lr', type=float, default=1e-3, help='Adam learning rate')
+    parser.add_argument('--gpu_id', type=int, default=0, help='GPU ID to use')
+    # additions
+    parser.add_argument('--synthetic', type=int, default=0, help='generate this many ZINC-shaped molecules')
+    parser.add_argument('--val_size', type=int, default=10000, help='held-out molecules (train_inductive.py:79)')
+    parser.add_argument('--seed', type=int, default=None)
+    parser.add_argument('--variational', action='store_true', help='train VGAE instead of GAE')
+    parser.add_argument('--dense_decoder', action='store_true', help="reference's materialised N x N loss")
+    parser.add_argument('--resume', type=str, default=None, help='checkpoint (ep{NN}.pkl or .ckpt) to resume from')
+    return parser
+
+
+def get_device(gpu_id: int) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("gae_dgl_b200 needs a CUDA device (B200); there is no CPU path")
+    return torch.device("cuda:{}".format(gpu_id))
+
+
+class Trainer:
+    def __init__(self, model, args, device=None):
+        self.model = model
+        self.device = device if device is not None else next(model.parameters()).device
+        self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr)
+        self.dense = bool(getattr(args, 'dense_decoder', False))
+        print('Total Parameters:', sum([p.nelement() for p in self.model.parameters()]))
+
+    def loss(self, g):
+        if not self.dense:
+            return self.model.loss(g)                       # fused K5/K6
+        adj = g.adjacency_matrix().to_dense().to(self.device)     # train_inductive.py:44
+        pos_weight = ((adj.shape[0] * adj.shape[0] - adj.sum()) / adj.sum())   # :46
+        adj_logits = self.model.forward(g)                  # :47
+        return BCELoss(adj_logits, adj, pos_weight=pos_weight)     # :48
+
+    def iteration(self, g, train=True):
+        loss = self.loss(g)
+        if train:
+            self.optim.zero_grad()
+            loss.backward()
+            self.optim.step()
+        return loss.item()
+
+    def save(self, epoch, save_dir):
+        output_path = os.path.join(save_dir, 'ep{:02}.pkl'.format(epoch))
+        torch.save(self.model.state_dict(), output_path)     # reference format (train_inductive.py:55-57)
+        torch.save({'epoch': epoch, 'model': self.model.state_dict(), 'optim': self.optim.state_dict()},
+                   os.path.join(save_dir, 'ep{:02}.ckpt'.format(epoch)))
+        return output_path
+
+    def load(self, path):
+        """Resume: accepts the reference's bare state_dict (.pkl) or the full .ckpt."""
+        st = torch.load(path, map_location=self.device)
+        if isinstance(st, dict) and 'model' in st and 'optim' in st:
+            self.model.load_state_dict(st['model'])
+            self.optim.load_state_dict(st['optim'])
+            return int(st.get('epoch', -1)) + 1
+        self.model.load_state_dict(st)
+        return 0
+
+
+def make_collate(device):
+    def collate(samples):
+        return dgl.batch(samples, device=device)             # train_inductive.py:31-35
+    return collate
+
+
+def load_graphs(args):
+    if args.synthetic:
+        from .synthetic import zinc_like_dataset
+        print('Generating {} synthetic ZINC-shaped molecules'.format(args.synthetic))
+        return zinc_like_dataset(args.synthetic, seed=args.seed or 0)
+    import dill
+    print('Loading data')
+    with open(args.data_file, 'rb') as f:
+        return dill.load(f)
+
+
+def plot(train_losses, val_losses, save_dir):
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return None
+    plt.plot(train_losses, label='train')
+    plt.plot(val_losses, label='val')
+    plt.legend()
+    plt.xlabel('epoch')
+    plt.ylabel('loss')
+    plt.grid()
+    out = os.path.join(save_dir, 'zinc250k.png')
+    plt.savefig(out)
+    return out
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    device = get_device(args.gpu_id)
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+    os.makedirs(args.save_dir, exist_ok=True)
+
+    model = (VGAE if args.variational else GAE)(args.in_dim, args.hidden_dims)
+    model.to(device)
+    graphs = load_graphs(args)
+    print('Loaded {} molecules'.format(len(graphs)))
+    from sklearn.model_selection import train_test_split
+    val_size = min(args.val_size, max(1, len(graphs) // 10))
+    train_graphs, val_graphs = train_test_split(graphs, test_size=val_size, random_state=args.seed)
+    train_dataset = MolDataset(train_graphs)
+    val_dataset = MolDataset(val_graphs)
+    del train_graphs, val_graphs
+
+    collate = make_collate(device)
+    train_loader = DataLoader(train_dataset, batch_size=args.batch_size, shuffle=True, collate_fn=collate)
+    val_loader = DataLoader(val_dataset, batch_size=args.batch_size, shuffle=False, collate_fn=collate)
+    trainer = Trainer(model, args, device)
+    start_epoch = trainer.load(args.resume) if args.resume else 0
+    train_losses, val_losses = [], []
+    print('Training Start')
+    for epoch in range(start_epoch, args.n_epochs):
+        train_loss = 0
+        model.train()
+        for bg in train_loader:
+            bg.set_e_initializer(dgl.init.zero_initializer)
+            bg.set_n_initializer(dgl.init.zero_initializer)
+            train_loss += trainer.iteration(bg)
+        train_loss /= len(train_loader)
+        train_losses.append(train_loss)
+        trainer.save(epoch, args.save_dir)
+
+        val_loss = 0
+        model.eval()
+        for bg in val_loader:
+            bg.set_e_initializer(dgl.init.zero_initializer)
+            bg.set_n_initializer(dgl.init.zero_initializer)
+            val_loss += trainer.iteration(bg, train=False)
+        val_loss /= len(val_loader)
+        val_losses.append(val_loss)
+        print('Epoch: {:02d} | Train Loss: {:.4f} | Validation Loss: {:.4f}'.format(epoch, train_loss, val_loss))
+    plot(train_losses, val_losses, args.save_dir)
+    return train_losses, val_losses
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,176 @@
+/* gae_b200.h -- C ABI of libgae_b200.so: the B200 (sm_100a) GAE encoder/decoder hot path.
+ *
+ * The reference (shionhonda/gae-dgl) has no FFI layer of its own: its hot path reaches
+ * native code through DGL's and PyTorch's operators.  Each entry point below replaces one
+ * of those operator calls; the citation is the reference call site (paths relative to
+ * /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - Every pointer named *_dev / without suffix is DEVICE memory unless the function name
+ *     ends in _host.  The caller owns every buffer, including workspaces; the library never
+ *     allocates or frees device memory (exception: the gae_ipc_* helpers map PEER memory).
+ *   - All launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  The device is the caller's current device.
+ *   - Return value: 0 = ok; negative = invalid argument (GAE_ERR_*); positive = cudaError_t.
+ *     gae_last_error_string() gives a per-thread human-readable message.  No C++ exception
+ *     crosses this boundary.  The library keeps no global mutable state besides tuning
+ *     knobs (gae_set_tuning) and the per-thread error string; it is re-entrant.
+ *   - Matrices are row-major fp32 with an explicit leading dimension (elements).  The
+ *     128-bit vector paths are taken when base pointers are 16-byte aligned and leading
+ *     dimensions are multiples of 4; otherwise a scalar path computes the same result.
+ *   - Graph indexing: CSR over DESTINATION rows, rowptr int64 [n_rows+1], col int32 [E] =
+ *     source ids, duplicates kept (multigraph), i.e. A[v,u] = #edges u->v, which is what
+ *     gae.py:18-19 sums and what DGL 0.4 adjacency_matrix() returns (train_inductive.py:44).
+ */
+#ifndef GAE_B200_H_
+#define GAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAE_OK 0
+#define GAE_ERR_INVALID_ARG (-1)
+#define GAE_ERR_UNSUPPORTED (-2)
+#define GAE_ERR_WORKSPACE (-3)
+
+#define GAE_ACT_IDENTITY 0 /* gae.py:43,45  lambda x: x */
+#define GAE_ACT_RELU 1     /* gae.py:36-41  F.relu      */
+
+/* ---- library ------------------------------------------------------------------------ */
+const char *gae_version(void);
+const char *gae_last_error_string(void);
+/* Tuning knobs used by bench sweeps ("spmm_variant", "spmm_unroll", "spmm_block", ...).
+ * Unknown keys return GAE_ERR_INVALID_ARG.  gae_get_tuning returns the value or -1. */
+int gae_set_tuning(const char *key, int32_t value);
+int32_t gae_get_tuning(const char *key);
+/* Number of kernels this library has launched from the calling process (for bench.py's
+ * "gpu_launches" claim). */
+int64_t gae_launch_count(void);
+
+/* ---- hub-row plan (host helper) ------------------------------------------------------- */
+/* Rows whose in-degree exceeds seg_len are split into ceil(deg/seg_len) segments that are
+ * summed by separate warps into a partial buffer and then reduced in fixed order
+ * (deterministic, atomics-free).  Two-call protocol on HOST rowptr:
+ *   1) gae_hub_plan_count_host -> n_long, n_seg
+ *   2) gae_hub_plan_fill_host  -> long_row[n_long], long_seg_ptr[n_long+1], seg_row[n_seg]
+ * The caller uploads the three arrays and passes them in gae_hub_plan_t. */
+int gae_hub_plan_count_host(const int64_t *rowptr_host, int64_t n_rows, int32_t seg_len,
+                            int64_t *n_long, int64_t *n_seg);
+int gae_hub_plan_fill_host(const int64_t *rowptr_host, int64_t n_rows, int32_t seg_len,
+                           int32_t *long_row, int64_t *long_seg_ptr, int32_t *seg_row);
+
+typedef struct gae_hub_plan_t {
+    int32_t seg_len;             /* edges per segment (> 0)                       */
+    int32_t _pad;
+    int64_t n_long;              /* rows with deg > seg_len                       */
+    int64_t n_seg;               /* total segments over those rows                */
+    const int32_t *long_row;     /* [n_long]   row id of k-th long row (ascending) */
+    const int64_t *long_seg_ptr; /* [n_long+1] prefix sum of segments per long row */
+    const int32_t *seg_row;      /* [n_seg]    index k of the long row a segment belongs to */
+} gae_hub_plan_t;
+
+/* ---- K1 / K2: CSR SpMM, Y = A X (sum aggregation) -------------------------------------- */
+/* Replaces  g.update_all(fn.copy_src('h','m'), fn.sum('m','h'))   gae.py:18-19,28
+ * and, called with CSR(A^T), its autograd adjoint dX = A^T dY      train_inductive.py:51.
+ *   vals       : optional per-edge weights [E] (NULL = unweighted, the reference's case)
+ *   plan       : optional hub-row plan (NULL = every row is summed by one warp)
+ *   partial_ws : [plan->n_seg, d] floats when plan != NULL and plan->n_seg > 0
+ *   accumulate : 0 -> Y = A X ; 1 -> Y += A X (used for the remote-source pass, 8e) */
+int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *vals,
+                     const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_rows,
+                     int32_t d, const gae_hub_plan_t *plan, float *partial_ws,
+                     int32_t accumulate, void *stream);
+
+/* Host-buffer variant (the e2e entry point): X_host -> device staging -> SpMM -> Y_host.
+ * rowptr/col/plan are DEVICE-resident graph state (the graph persists across epochs in the
+ * reference, train_transductive.py:45; features are re-assigned every epoch).  X_host and
+ * Y_host should be pinned.  X_stage [n_src,ldx] and Y_stage [n_rows,ldy] are caller-owned
+ * device buffers.  Copies and kernels are enqueued on `stream`; returns without syncing. */
+int gae_spmm_csr_f32_host(const int64_t *rowptr, const int32_t *col, const float *X_host,
+                          int64_t n_src, int64_t ldx, float *Y_host, int64_t ldy,
+                          int64_t n_rows, int32_t d, const gae_hub_plan_t *plan,
+                          float *partial_ws, float *X_stage, float *Y_stage, void *stream);
+
+/* ---- K3: NodeApplyModule = Linear + activation ------------------------------------------ */
+/* Replaces  h = self.linear(node.data['h']); h = self.activation(h)   gae.py:13-16.
+ * H[n,d_out] = act(Yin[n,d_in] W^T + b), W is [d_out,d_in] row-major (nn.Linear layout). */
+int gae_linear_fwd_f32(const float *Yin, int64_t ld_in, const float *W, const float *b,
+                       float *H, int64_t ld_out, int64_t n, int32_t d_in, int32_t d_out,
+                       int32_t act, void *stream);
+/* Adjoint.  H is the forward OUTPUT (post-activation; the ReLU mask is H > 0).
+ * dYin may be NULL (first layer: input features are a leaf, gae.py:50).
+ * ws: gae_linear_bwd_ws_bytes() bytes.  dW [d_out,d_in], db [d_out] are overwritten. */
+int64_t gae_linear_bwd_ws_bytes(int64_t n, int32_t d_in, int32_t d_out);
+int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *W, const float *H,
+                       int64_t ld_out, const float *dH, int64_t ld_dh, float *dYin,
+                       int64_t ld_dyin, float *dW, float *db, void *ws, int64_t ws_bytes,
+                       int64_t n, int32_t d_in, int32_t d_out, int32_t act, void *stream);
+
+/* ---- K4: dropout (always on in the reference decoder) ------------------------------------ */
+/* Replaces  z = F.dropout(z, self.dropout)   gae.py:70  (training=True regardless of mode).
+ * mask_mode 0: draw keep-mask from Philox4x32-10(seed, offset) and WRITE it to mask (u8);
+ * mask_mode 1: READ the given keep-mask (parity tests inject the oracle's mask).
+ * Zd = Z * mask / (1-p).  Z/Zd are [n,d] with leading dimensions. */
+int gae_dropout_fwd_f32(const float *Z, int64_t ldz, float *Zd, int64_t ldzd, uint8_t *mask,
+                        int64_t n, int32_t d, float p, uint64_t seed, uint64_t offset,
+                        int32_t mask_mode, void *stream);
+/* dZ = dZd * mask / (1-p) * (*grad_scale or 1 if NULL)  */
+int gae_dropout_bwd_f32(const float *dZd, int64_t ld_dzd, const uint8_t *mask, float *dZ,
+                        int64_t ld_dz, int64_t n, int32_t d, float p, const float *grad_scale,
+                        void *stream);
+
+/* ---- K5 / K6: fused InnerProductDecoder + weighted BCE-with-logits ------------------------- */
+/* Replaces  torch.mm(z, z.t())                               gae.py:71
+ *           adj = g.adjacency_matrix().to_dense()            train_inductive.py:44
+ *           BCELoss(adj_logits, adj, pos_weight=pos_weight)  train_inductive.py:48
+ * without materialising any N x N array:
+ *   L = (1/N^2) [ sum_ij softplus(x_ij) + sum_{e=(i,j)} (pw softplus(-x_ij) - softplus(x_ij)) ],
+ *   x_ij = <Zd_i, Zd_j>, the edge sum running over the CSR with multiplicity.
+ * mode bit0: compute loss -> *loss (device scalar)
+ * mode bit1: compute dZd_unit = dL/dZd for grad_loss = 1 (needs rowptr_t/col_t = CSR(A^T))
+ * d <= 128.  ws: gae_decoder_ws_bytes(n, d) bytes. */
+#define GAE_DEC_LOSS 1
+#define GAE_DEC_GRAD 2
+int64_t gae_decoder_ws_bytes(int64_t n, int32_t d);
+int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d,
+                        const int64_t *rowptr, const int32_t *col, const int64_t *rowptr_t,
+                        const int32_t *col_t, float pos_weight, int32_t mode, float *loss,
+                        float *dZd_unit, int64_t ld_dz, void *ws, int64_t ws_bytes,
+                        void *stream);
+/* Materialised logits X = Zd Zd^T [n,n] (the value GAE.forward returns, gae.py:54-55). */
+int gae_decoder_logits_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, float *X,
+                           int64_t ldx, void *stream);
+
+/* ---- graph indexing on device ("bit-exact adjacency/degree indexing") ---------------------- */
+/* in_degrees (train_transductive.py:55): deg[v] = rowptr[v+1]-rowptr[v] as int64. */
+int gae_in_degrees_i64(const int64_t *rowptr, int64_t n_rows, int64_t *deg, void *stream);
+/* dgl.batch (train_inductive.py:34): block-diagonal union of K CSR graphs already
+ * concatenated back to back: col_cat [E_total] holds each graph's LOCAL source ids,
+ * edge_graph_ptr [K+1] the edge offsets, node_off [K+1] the node prefix sums.  Adds the node
+ * offset of its graph to every col entry (in place). */
+int gae_batch_offset_cols_i32(int32_t *col_cat, const int64_t *edge_graph_ptr,
+                              const int64_t *node_off, int64_t n_graphs, int64_t n_edges,
+                              void *stream);
+
+/* ---- K7: halo exchange helpers (8e) -------------------------------------------------------- */
+/* Pack rows idx[0..m) of X into out (send buffer of the all-to-all-v). */
+int gae_gather_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t m, int32_t d,
+                        float *out, int64_t ld_out, void *stream);
+/* One-sided halo pull over NVLink peer memory: for i in [0,m): out[i,:] = peer_base[owner
+ * slot][idx[i],:], where peer_ptrs is a device array of P mapped base pointers (own rank's
+ * slot may be its local pointer) and owner[i] selects the slot. */
+int gae_pull_rows_p2p_f32(const float *const *peer_ptrs, const int32_t *owner,
+                          const int64_t *idx, int64_t m, int64_t ldx, int32_t d, float *out,
+                          int64_t ld_out, void *stream);
+/* CUDA IPC plumbing for the pull path: 64-byte handles. */
+int gae_ipc_get_handle(const void *dev_ptr, uint8_t handle_out[64], int64_t *offset_out);
+int gae_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out);
+int gae_ipc_close_handle(void *dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAE_B200_H_ */
