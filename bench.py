@@ -1,0 +1,498 @@
+#!/usr/bin/env python
+"""Benchmark of the GAE hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3] at N=1, configs[4] at N=8; weak scaling in between):
+Graph500 R-MAT (a,b,c,d = .57,.19,.19,.05), scale 22+log2(N), |E| = 1e8 * N directed edges,
+no dedup, vertex labels scrambled (Graph500), d = 64 fp32 features.  One "step" is the
+encoder aggregation train step on that graph: SpMM forward Y = A X followed by SpMM backward
+dX = A^T dY (the N^2 decoder is infeasible at |V| >= 4M and is not run).
+metric = |E| / step time.  The Pubmed train step (configs[1]) is reported in the same line
+under "pubmed".
+
+--impl reference times the CPU oracle (the reference's DGL path cannot be installed here:
+no dgl wheel, no network) with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+D_FEAT = 64
+BASE_SCALE = 22
+BASE_EDGES = 100_000_000
+METRIC = "GAE train-step edges/sec (RMAT SpMM fwd+bwd, d=64)"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    p.add_argument("--base-scale", type=int, default=BASE_SCALE, help="log2 |V| per GPU")
+    p.add_argument("--base-edges", type=int, default=BASE_EDGES, help="|E| per GPU")
+    p.add_argument("--cpu-sample-div", type=int, default=8, help="CPU legs use |E|/div edges of the same stream")
+    p.add_argument("--no-pubmed", action="store_true")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--exchange", type=str, default="auto", choices=["auto", "nccl", "p2p"])
+    p.add_argument("--tune", type=str, default="", help="comma list key=value for gae_set_tuning")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def spmm_algorithmic_bytes(n_edges: int, n_rows: int, d: int) -> int:
+    """SURVEY.md 8d primary (gather) model: per edge 4 B col + 4d B source row; per row 4d B
+    output + 4 B rowptr  ->  260 B/edge + 260 B/row at d = 64."""
+    return n_edges * (4 + 4 * d) + n_rows * (4 * d + 4)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (pynvml, falling back to nvidia-smi)
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake"}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (oracle)
+# ------------------------------------------------------------------------------------------
+
+def cpu_rmat_leg(scale: int, sample_edges: int, steps: int, warmup: int, total_edges: int):
+    """Times the oracle's SpMM fwd + bwd (the reference's update_all(copy_src,sum) and its
+    adjoint) on the first `sample_edges` edges of the workload's edge stream, all host threads.
+    Two restatements are timed -- torch.sparse CSR (MKL) and the OpenMP C loop -- the faster is
+    reported."""
+    from gae_dgl_b200 import synthetic
+    from gae_dgl_b200.graph import coo_to_csr_torch
+    from oracle import c_spmm
+    from oracle import gae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 1 << scale
+    src, dst = synthetic.rmat_edges(scale, sample_edges, seed=1, device="cpu")
+    rowptr, col = coo_to_csr_torch(src, dst, n)
+    rowptr_t, col_t = coo_to_csr_torch(dst, src, n)
+    del src, dst
+    # feature VALUES do not affect timing; torch.rand is used on the host to keep set-up short
+    X = torch.rand(n, D_FEAT, generator=torch.Generator().manual_seed(2))
+    dY = torch.rand(n, D_FEAT, generator=torch.Generator().manual_seed(3))
+    rp, cl, rpt, clt = rowptr.numpy(), col.numpy(), rowptr_t.numpy(), col_t.numpy()
+    Xn, dYn = X.numpy(), dY.numpy()
+
+    def step_c():
+        c_spmm.spmm_f32(rp, cl, Xn)
+        c_spmm.spmm_f32(rpt, clt, dYn)
+
+    A = torch.sparse_csr_tensor(rowptr, col.to(torch.int64), torch.ones(col.numel()), size=(n, n))
+    At = torch.sparse_csr_tensor(rowptr_t, col_t.to(torch.int64), torch.ones(col_t.numel()), size=(n, n))
+
+    def step_torch():
+        A @ X
+        At @ dY
+
+    results = {}
+    for name, fn in (("openmp_c", step_c), ("torch_sparse_csr", step_torch)):
+        for _ in range(max(1, min(warmup, 2))):
+            fn()
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        results[name] = statistics.median(ts)
+    best = min(results, key=results.get)
+    return {
+        "value": sample_edges / results[best], "unit": "edges/s", "cores": cores, "kind": "port",
+        "sample": f"first {sample_edges} of {total_edges} edges of the same R-MAT stream (scale {scale}, |V|={n}), "
+                  f"SpMM fwd+bwd d={D_FEAT}, {best}, median of {steps}",
+        "ms_per_step": results[best] * 1e3,
+        "variants_ms": {k: v * 1e3 for k, v in results.items()},
+    }
+
+
+def cpu_pubmed_leg(steps: int = 2):
+    """Reference train step on the Pubmed-shaped graph on the host: dense adj, encoder, dropout,
+    Z Z^T, weighted BCE, backward, Adam (train_transductive.py:55-68 repaired)."""
+    from gae_dgl_b200 import synthetic
+    from oracle import gae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g, X = synthetic.planetoid_like("pubmed", seed=0)
+    c = g.csr()
+    torch.manual_seed(0)
+    model = O.OracleGAE(500, [32, 16])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        adj = O.dense_adj_from_csr(c.rowptr, c.col)
+        pw = O.pos_weight_transductive(adj)
+        loss = O.bce_loss(model(c.rowptr, c.col, X), adj, pw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    return {"value": g.number_of_edges() / t, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"full Pubmed-shaped train step, best of {steps}", "ms_per_step": t * 1e3}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = args.gpus
+    scale = args.base_scale + int(round(math.log2(n_gpus)))
+    total = args.base_edges * n_gpus
+    sample = max(1, args.base_edges // args.cpu_sample_div)
+    leg = cpu_rmat_leg(scale, sample, args.steps, args.warmup, total)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "edges/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rmat_scale{scale}_E{total}_d{D_FEAT}", "step": "spmm_fwd+spmm_bwd",
+                   "note": "reference = CPU oracle port (DGL not installable: no wheel, no network)"},
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": leg["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "variants_ms": leg["variants_ms"],
+    }
+    if not args.no_pubmed and n_gpus == 1:
+        line["pubmed"] = cpu_pubmed_leg()
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+
+def cuda_time_ms(fn, steps, stream):
+    """K calls bracketed by events on the launching stream; returns total ms."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def pubmed_leg(dev, steps=50, warmup=5):
+    import gae_dgl_b200 as G
+    from gae_dgl_b200 import synthetic
+    g, X = synthetic.planetoid_like("pubmed", seed=0)
+    torch.manual_seed(0)
+    model = G.GAE(500, [32, 16]).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    g.to(dev)
+    Xd = X.to(dev)
+    pw = G.pos_weight_of(g, transductive=True)
+    st = torch.cuda.current_stream()
+
+    def step():
+        g.ndata["h"] = Xd
+        loss = model.loss(g, pos_weight=pw)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ms = cuda_time_ms(step, steps, st) / steps
+    # e2e: features from pinned host memory every step, loss read back every step
+    Xp = X.pin_memory()
+
+    def step_e2e():
+        g.ndata["h"] = Xp.to(dev, non_blocking=True)
+        loss = model.loss(g, pos_weight=pw)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    e = g.number_of_edges()
+    return {"workload": "pubmed_like_N19717_E88651_F500 train step (fwd+bwd+Adam, fused decoder)",
+            "value": e / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
+            "e2e": {"value": e / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(X.numel() * 4), "d2h_bytes_per_step": 4}}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import gae_dgl_b200 as G
+    from gae_dgl_b200 import _lib, ops, synthetic
+    from gae_dgl_b200.graph import coo_to_csr_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        _lib.set_tuning(k, int(v))
+
+    scale = args.base_scale + int(round(math.log2(world)))
+    n = 1 << scale
+    total_edges = args.base_edges * world
+    stream = torch.cuda.current_stream()
+
+    if world == 1:
+        src, dst = synthetic.rmat_edges(scale, total_edges, seed=1, device=dev)
+        rowptr, col = coo_to_csr_torch(src, dst, n)
+        rowptr_t, col_t = coo_to_csr_torch(dst, src, n)
+        del src, dst
+        torch.cuda.empty_cache()
+        g = G.DGLGraph.from_csr(rowptr, col, csr_t=(rowptr_t, col_t))
+        c, t = g.csr(), g.csr_t()
+        X = synthetic.hashed_normal(n, D_FEAT, 2, device=dev)
+        dY = synthetic.hashed_normal(n, D_FEAT, 3, device=dev)
+        Y = torch.empty_like(X)
+        dX = torch.empty_like(X)
+        ws_f = c.plan.workspace(D_FEAT, dev)
+        ws_b = t.plan.workspace(D_FEAT, dev)
+        local_edges = total_edges
+        local_rows = n
+
+        def fwd():
+            ops.spmm(c.rowptr, c.col, X, c.plan, out=Y, partial_ws=ws_f)
+
+        def bwd():
+            ops.spmm(t.rowptr, t.col, dY, t.plan, out=dX, partial_ws=ws_b)
+
+        exchange_desc = "none (single GPU)"
+        halo_rows = 0
+    else:
+        from gae_dgl_b200 import parallel
+        part = parallel.build_rmat_partition(scale, total_edges, seed=1, d=D_FEAT, device=dev,
+                                             exchange=args.exchange)
+        fwd, bwd = part.fwd, part.bwd
+        local_edges, local_rows = part.local_edges, part.local_rows
+        exchange_desc = part.exchange_desc
+        halo_rows = part.halo_rows
+
+    def step():
+        fwd()
+        bwd()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, barrier + synchronize on both sides, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        fwd()
+        ev[2 * i + 1].record(stream)
+        bwd()
+        ev[2 * i + 2].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop()
+    launches = _lib.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    fwd_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]
+    bwd_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
+    t = torch.tensor([total_ms, statistics.mean(fwd_ms), statistics.mean(bwd_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fwd_mean, bwd_mean = (float(x) for x in t)
+    ms_per_step = total_ms / args.steps
+    value = total_edges / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMM forward), per rank
+    peak, peak_src = peaks()
+    alg_bytes = spmm_algorithmic_bytes(local_edges, local_rows, D_FEAT)
+    # the fwd event pair brackets the row kernel + hub-segment kernel + hub reduce (+ exchange at N>1)
+    achieved = alg_bytes / (statistics.mean(fwd_ms) * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "spmm_vec_kernel (fwd: rows + hub segments + hub reduce)",
+                "algorithmic_bytes": alg_bytes, "fwd_ms": statistics.mean(fwd_ms), "bwd_ms": statistics.mean(bwd_ms),
+                "peak_source": peak_src}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rmat_scale{scale}_E{total_edges}_d{D_FEAT}", "step": "spmm_fwd+spmm_bwd",
+                   "rmat": "a=.57 b=.19 c=.19 d=.05, no dedup, labels scrambled, seed 1",
+                   "partition": "1d_vertex_blocks" if world > 1 else "single", "exchange": exchange_desc,
+                   "halo_rows_rank0": halo_rows,
+                   "l2": f"inputs {4 * D_FEAT * local_rows / 1e6:.0f} MB features + {4 * local_edges / 1e6:.0f} MB indices "
+                         ">> 126 MB L2, no flush between iterations",
+                   "tuning": {k: _lib.get_tuning(k) for k in ("spmm_unroll", "spmm_block", "spmm_cache",
+                                                              "spmm_rows_per_warp")}},
+        "roofline": roofline, "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "fwd_ms_max_over_ranks": fwd_mean, "bwd_ms_max_over_ranks": bwd_mean,
+    }
+
+    # ---- e2e: host buffers through the C ABI entry point, copies inside the timed region
+    if not args.no_e2e and world == 1:
+        line["e2e"] = e2e_leg(c, t, X, dY, n, total_edges, min(args.steps, 10), dev, ws_f, ws_b)
+    elif not args.no_e2e:
+        line["e2e"] = part.e2e(min(args.steps, 10))
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        del X, dY
+        torch.cuda.empty_cache()
+        sample = max(1, args.base_edges // args.cpu_sample_div)
+        leg = cpu_rmat_leg(scale, sample, 3, 1, total_edges)
+        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_pubmed:
+            line["pubmed"] = pubmed_leg(dev)
+            line["pubmed"]["cpu_baseline"] = cpu_pubmed_leg()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_leg(c, t, X, dY, n, total_edges, steps, dev, ws_f, ws_b):
+    """Same step through gae_spmm_csr_f32_host: features / gradients live in PINNED HOST memory,
+    results are returned to pinned host memory; the graph (CSR, CSR^T, hub plans) is resident
+    device state, as the DGLGraph is across epochs in the reference."""
+    import ctypes
+    from gae_dgl_b200 import _lib
+    lib = _lib.load()
+    Xh = torch.empty((n, D_FEAT), dtype=torch.float32, pin_memory=True)
+    dYh = torch.empty((n, D_FEAT), dtype=torch.float32, pin_memory=True)
+    Yh = torch.empty((n, D_FEAT), dtype=torch.float32, pin_memory=True)
+    dXh = torch.empty((n, D_FEAT), dtype=torch.float32, pin_memory=True)
+    Xh.copy_(X)
+    dYh.copy_(dY)
+    Xs, Ys = torch.empty_like(X), torch.empty_like(X)
+    stream = torch.cuda.current_stream()
+    p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None  # noqa: E731
+
+    def call(csr, src_h, dst_h, ws):
+        rc = lib.gae_spmm_csr_f32_host(p(csr.rowptr), p(csr.col), p(src_h), n, D_FEAT, p(dst_h), D_FEAT, n, D_FEAT,
+                                       ctypes.byref(csr.plan.struct) if csr.plan.n_seg else None, p(ws), p(Xs), p(Ys),
+                                       stream.cuda_stream)
+        _lib.check(rc, "gae_spmm_csr_f32_host")
+
+    def step():
+        call(c, Xh, Yh, ws_f)
+        call(t, dYh, dXh, ws_b)
+
+    step()
+    torch.cuda.synchronize()
+    ms = cuda_time_ms(step, steps, stream) / steps
+    ok = bool(torch.isfinite(Yh[:1024]).all())
+    return {"value": total_edges / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": int(2 * n * D_FEAT * 4), "d2h_bytes_per_step": int(2 * n * D_FEAT * 4),
+            "api": "gae_spmm_csr_f32_host (C ABI), pinned host X/dY in, Y/dX out; graph resident", "finite": ok}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

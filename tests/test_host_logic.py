@@ -1,0 +1,194 @@
+"""CPU: host logic, the graph container, and that the C-ABI library loads and exports every
+symbol include/gae_b200.h declares (no compute calls here -- there is no GPU)."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import gae_dgl_b200 as G
+from gae_dgl_b200 import _lib, ops, synthetic
+from gae_dgl_b200.graph import coo_to_csr_numpy, coo_to_csr_torch
+from oracle import gae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "gae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    names = header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/gae_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES.keys()) == names, "ctypes table and header disagree"
+    assert "sm_100a" in _lib.version()
+
+
+def test_sass_is_sm100a_only(lib_built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_built], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_error_codes_and_tuning(lib_built):
+    lib = _lib.load()
+    assert lib.gae_set_tuning(b"no_such_knob", 1) == -1
+    assert b"no_such_knob" in lib.gae_last_error_string()
+    _lib.set_tuning("spmm_unroll", 4)
+    assert _lib.get_tuning("spmm_unroll") == 4
+    _lib.set_tuning("spmm_unroll", 8)
+    with pytest.raises(_lib.GaeError):
+        _lib.check(lib.gae_hub_plan_count_host(None, 0, 0, None, None), "plan")
+
+
+def test_ops_refuse_cpu_tensors(lib_built):
+    with pytest.raises(G.GaeError):
+        ops.spmm(torch.zeros(2, dtype=torch.int64), torch.zeros(0, dtype=torch.int32), torch.zeros(1, 4))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GaeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_hub_plan_host_matches_numpy(lib_built):
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 40, size=500)
+    deg[[3, 77, 400]] = [1000, 513, 512]
+    rowptr = np.zeros(501, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    plan = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=512)
+    assert plan.n_long == 2 and plan.long_row[:2].tolist() == [3, 77]
+    assert plan.long_seg_ptr.tolist() == [0, 2, 4] and plan.seg_row.tolist() == [0, 0, 1, 1]
+    plan = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=16)
+    long = np.flatnonzero(deg > 16)
+    assert plan.long_row.tolist() == long.tolist()
+    assert plan.n_seg == int(np.sum((deg[long] + 15) // 16))
+
+
+def test_graph_container_matches_oracle_indexing():
+    rng = np.random.default_rng(1)
+    n, e = 50, 300
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    g = G.DGLGraph()
+    g.add_nodes(n)
+    g.add_edges(src[:100], dst[:100])
+    g.add_edges(torch.from_numpy(src[100:]), torch.from_numpy(dst[100:]))
+    rp, col = O.coo_to_csr(torch.from_numpy(src), torch.from_numpy(dst), n)
+    c = g.csr()
+    assert torch.equal(c.rowptr, rp) and torch.equal(c.col, col)
+    rt, ct = O.csr_transpose(rp, col)
+    t = g.csr_t()
+    assert torch.equal(t.rowptr, rt) and torch.equal(t.col, ct)
+    assert torch.equal(g.in_degrees(), O.in_degrees(rp))
+    assert torch.equal(g.adjacency_matrix().to_dense(), O.dense_adj(torch.from_numpy(src), torch.from_numpy(dst), n))
+    assert g.number_of_edges() == e and g.number_of_nodes() == n
+    r2, c2 = coo_to_csr_torch(torch.from_numpy(src), torch.from_numpy(dst), n)
+    assert torch.equal(r2, rp) and torch.equal(c2, col)
+
+
+def test_graph_edge_cases():
+    g = G.DGLGraph()
+    g.add_nodes(4)
+    assert g.csr().rowptr.tolist() == [0] * 5 and g.csr().col.numel() == 0
+    g.add_edges(0, [1, 2, 3])       # scalar broadcast, like DGL
+    assert g.in_degrees().tolist() == [0, 1, 1, 1]
+    with pytest.raises(G.GaeError):
+        g.add_edges([0], [4])
+    with pytest.raises(G.GaeError):
+        g.update_all(lambda e: e, lambda n: n)
+
+
+def test_networkx_constructor_mirrors_undirected_edges():
+    import networkx as nx
+    nxg = nx.Graph()
+    nxg.add_nodes_from(range(4))
+    nxg.add_edges_from([(0, 1), (1, 2), (3, 3)])
+    g = G.DGLGraph(nxg)
+    assert g.number_of_edges() == 5          # 2 x 2 mirrored + 1 self loop
+    assert g.adjacency_matrix().to_dense().tolist() == [[0, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]
+
+
+def test_batch_matches_oracle_and_pickles():
+    ds = synthetic.zinc_like_dataset(8, seed=3)
+    bg = G.batch(ds)
+    s, d, n = O.batch_graphs([(*g.edges(), g.number_of_nodes()) for g in ds])
+    rp, col = O.coo_to_csr(s, d, n)
+    assert bg.number_of_nodes() == n
+    assert torch.equal(bg.csr().rowptr, rp) and torch.equal(bg.csr().col, col)
+    assert torch.equal(bg.ndata["h"], torch.cat([g.ndata["h"] for g in ds]))
+    assert bg.batch_num_nodes == [g.number_of_nodes() for g in ds]
+    bg2 = pickle.loads(pickle.dumps(bg))
+    assert torch.equal(bg2.csr().col, col) and torch.equal(bg2.ndata["h"], bg.ndata["h"])
+    import dill
+    g0 = dill.loads(dill.dumps(ds[0]))
+    assert g0.number_of_edges() == ds[0].number_of_edges()
+
+
+def test_zinc_like_shapes():
+    ds = synthetic.zinc_like_dataset(200, seed=0)
+    nodes = np.mean([g.number_of_nodes() for g in ds])
+    edges = np.mean([g.number_of_edges() for g in ds])
+    assert 21 < nodes < 25 and 44 < edges < 56
+    for g in ds[:20]:
+        assert g.ndata["h"].shape[1] == 39 and int(g.in_degrees().max()) <= 4
+        a = g.adjacency_matrix().to_dense()
+        assert torch.equal(a, a.t())                       # both directions (prepare_data.py:61-64)
+        assert torch.equal(g.ndata["h"][:, :23].sum(1), torch.ones(g.number_of_nodes()))
+
+
+def test_planetoid_like_shapes():
+    g, x = synthetic.planetoid_like("cora", seed=0)
+    assert g.number_of_nodes() == 2708 and g.number_of_edges() == 10556 and x.shape == (2708, 1433)
+    assert torch.allclose(x.sum(1), torch.ones(2708), atol=1e-5)
+    a = g.csr()
+    t = g.csr_t()
+    assert torch.equal(a.rowptr, t.rowptr) and torch.equal(a.col, t.col)   # symmetric
+
+
+def test_rmat_is_deterministic_and_prefix_stable():
+    s, d = synthetic.rmat_edges(14, 5000, seed=1)
+    s2, d2 = synthetic.rmat_edges(14, 2000, seed=1, first_edge=1000, chunk=512)
+    assert torch.equal(s[1000:3000], s2) and torch.equal(d[1000:3000], d2)
+    assert int(s.max()) < 1 << 14 and int(s.min()) >= 0
+    v = torch.arange(1 << 12)
+    assert synthetic.scramble(v, 12, 5).unique().numel() == 1 << 12
+    # skew survives the relabelling: some vertex collects far more than the mean in-degree
+    sb, db = synthetic.rmat_edges(14, 200000, seed=1)
+    deg = torch.bincount(db, minlength=1 << 14)
+    assert deg.max() > 20 * deg.float().mean() and (deg == 0).float().mean() > 0.2
+    x = synthetic.hashed_normal(64, 8, 2)
+    assert torch.equal(x[10:20], synthetic.hashed_normal(10, 8, 2, first_row=10))
+
+
+def test_module_surface_and_state_dict():
+    m = G.GAE(39, [32, 16])
+    assert list(m.state_dict().keys()) == list(O.OracleGAE(39, [32, 16]).state_dict().keys())
+    m.load_state_dict(O.OracleGAE(39, [32, 16]).state_dict())
+    assert isinstance(m.layers[0], G.GCN) and isinstance(m.layers[0].apply_mod, G.NodeApplyModule)
+    assert isinstance(m.decoder, G.InnerProductDecoder) and m.decoder.dropout == 0.1
+    assert m.layers[0].apply_mod.activation is torch.nn.functional.relu
+    assert m.layers[1].apply_mod.activation(3) == 3
+    one = G.GAE(8, [4])
+    assert len(one.layers) == 1 and one.layers[0].apply_mod.activation(5) == 5
+    v = G.VGAE(39, [32, 16])
+    assert v.mu_head.apply_mod.linear.weight.shape == (16, 32)
+
+
+def test_pos_weight_matches_reference_expression():
+    g, _ = synthetic.planetoid_like("cora", seed=0)
+    adj = g.adjacency_matrix().to_dense()
+    assert G.pos_weight_of(g) == float(O.pos_weight_inductive(adj))
+    assert G.pos_weight_of(g, transductive=True) == float(O.pos_weight_transductive(adj)[0])

@@ -1,0 +1,160 @@
+"""CPU: pins the oracle (SURVEY.md section 8c known-answer tests + committed golden vectors)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import gae_oracle as O
+from oracle import c_spmm
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "gae_small.npz")
+
+
+def test_pin_dropout_always_on_and_scaled():
+    # pin (1): F.dropout(z, 0.1) with default args drops ~10 % and scales by 1/0.9, train or eval
+    torch.manual_seed(0)
+    z = torch.ones(200, 50)
+    out = F.dropout(z, 0.1)
+    kept = out != 0
+    assert 0.85 < kept.float().mean() < 0.95
+    assert torch.allclose(out[kept], torch.full_like(out[kept], 1 / 0.9))
+    mask = kept
+    assert torch.equal(O.apply_dropout_mask(z, mask, 0.1), out)
+
+
+def test_pin_coo_to_dense_sums_duplicates():
+    # pin (2): edges {(0,1),(0,1),(1,0)} as (dst,src) index pairs -> [[0,2],[1,0]]
+    src = torch.tensor([1, 1, 0])
+    dst = torch.tensor([0, 0, 1])
+    assert O.dense_adj(src, dst, 2).tolist() == [[0.0, 2.0], [1.0, 0.0]]
+
+
+def test_pin_sparse_form_identity_and_gradient():
+    # pin (3): closed form == F.binary_cross_entropy_with_logits(..., pos_weight), incl. multigraph y=2
+    g = torch.Generator().manual_seed(3)
+    n = 40
+    src = torch.randint(0, n, (150,), generator=g)
+    dst = torch.randint(0, n, (150,), generator=g)
+    src = torch.cat([src, src[:10]])
+    dst = torch.cat([dst, dst[:10]])            # duplicates -> y = 2
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    adj = O.dense_adj(src, dst, n, torch.float64)
+    assert adj.max() >= 2
+    z = torch.randn(n, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    pw = float(O.pos_weight_inductive(adj))
+    ref = F.binary_cross_entropy_with_logits(z @ z.t(), adj, pos_weight=torch.tensor(pw, dtype=torch.float64))
+    alt = O.bce_loss_sparse_form(z, rowptr, col, pw)
+    assert abs(float(ref) - float(alt)) < 1e-12 * max(1.0, abs(float(ref)))
+    g1, = torch.autograd.grad(ref, z, retain_graph=True)
+    g2, = torch.autograd.grad(alt, z)
+    assert torch.allclose(g1, g2, rtol=1e-10, atol=1e-14)
+    # analytic gradient of SURVEY.md 8a row 6
+    x = (z @ z.t()).detach()
+    s = torch.sigmoid(x)
+    G = ((1 - adj) * s - pw * adj * (1 - s)) / (n * n)
+    assert torch.allclose(g1, (G + G.t()) @ z.detach(), rtol=1e-9, atol=1e-13)
+
+
+def test_pin_linear_init_and_param_counts():
+    # pins (4), (5)
+    lin = nn.Linear(39, 32)
+    assert lin.weight.abs().max() <= 1 / np.sqrt(39) + 1e-7
+    count = lambda m: sum(p.numel() for p in m.parameters())
+    assert count(O.OracleGAE(39, [32, 16])) == 1808
+    assert count(O.OracleGAE(500, [32, 16])) == 16560
+    assert count(O.OracleGAE(1433, [32, 16])) == 46416
+    assert O.relu_flags(1) == [False] and O.relu_flags(3) == [True, True, False]
+    assert list(O.OracleGAE(39, [32, 16]).state_dict().keys()) == [
+        "layers.0.apply_mod.linear.weight", "layers.0.apply_mod.linear.bias",
+        "layers.1.apply_mod.linear.weight", "layers.1.apply_mod.linear.bias"]
+
+
+def test_spmm_hand_graph():
+    # edges u->v: 0->1, 0->1 (dup), 2->1, 1->0 ; node 2 has no in-edge
+    src = torch.tensor([0, 0, 2, 1])
+    dst = torch.tensor([1, 1, 1, 0])
+    rowptr, col = O.coo_to_csr(src, dst, 3)
+    assert rowptr.tolist() == [0, 1, 4, 4] and col.tolist() == [1, 0, 0, 2]
+    X = torch.tensor([[1.0, 10.0], [2.0, 20.0], [4.0, 40.0]])
+    Y = O.spmm_sum(rowptr, col, X)
+    assert Y.tolist() == [[2.0, 20.0], [6.0, 60.0], [0.0, 0.0]]
+    assert torch.equal(O.dense_adj(src, dst, 3) @ X, Y)
+    assert O.in_degrees(rowptr).tolist() == [1, 3, 0]
+    rt, ct = O.csr_transpose(rowptr, col)
+    assert rt.tolist() == [0, 2, 3, 4] and ct.tolist() == [1, 1, 0, 1]
+
+
+def test_spmm_variants_agree():
+    g = torch.Generator().manual_seed(5)
+    n, e = 300, 3000
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, n, (e,), generator=g)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    X = torch.randn(n, 24, generator=g)
+    y64 = O.spmm_sum(rowptr, col, X.double())
+    assert torch.allclose(O.spmm_sum(rowptr, col, X).double(), y64, atol=1e-4)
+    assert torch.allclose(O.spmm_sum_sparse(rowptr, col, X).double(), y64, atol=1e-4)
+    assert torch.allclose((O.dense_adj(src, dst, n, torch.float64) @ X.double()), y64, atol=1e-10)
+    yc = c_spmm.spmm_f32(rowptr.numpy(), col.numpy(), X.numpy())
+    assert np.allclose(yc, y64.numpy(), atol=1e-4)
+    yc64 = c_spmm.spmm_f64acc(rowptr.numpy(), col.numpy(), X.numpy())
+    assert np.allclose(yc64, y64.numpy(), atol=1e-12)
+
+
+def test_batch_is_block_diagonal():
+    g1 = (torch.tensor([0, 1]), torch.tensor([1, 0]), 2)
+    g2 = (torch.tensor([0, 2]), torch.tensor([1, 1]), 3)
+    s, d, n = O.batch_graphs([g1, g2])
+    assert n == 5 and s.tolist() == [0, 1, 2, 4] and d.tolist() == [1, 0, 3, 3]
+    A = O.dense_adj(s, d, n)
+    assert A[:2, 2:].abs().sum() == 0 and A[2:, :2].abs().sum() == 0
+
+
+def test_pos_weight_forms():
+    adj = torch.zeros(10, 10)
+    adj[0, 1] = adj[1, 0] = 1
+    adj[2, 3] = 2
+    a = O.pos_weight_inductive(adj)
+    b = O.pos_weight_transductive(adj)
+    assert a.dim() == 0 and b.shape == (1,)
+    assert abs(float(a) - 24.0) < 1e-6 and abs(float(b) - 24.0) < 1e-6
+
+
+def test_golden_vectors_reproduce():
+    z = np.load(GOLDEN)
+    rowptr, col = O.coo_to_csr(torch.from_numpy(z["src"]), torch.from_numpy(z["dst"]), int(z["n"]))
+    assert np.array_equal(rowptr.numpy(), z["rowptr"]) and np.array_equal(col.numpy(), z["col"])
+    X = torch.from_numpy(z["X"])
+    assert np.allclose(O.spmm_sum(rowptr, col, X.double()).numpy(), z["spmm64"], atol=1e-12)
+    weights = [(torch.from_numpy(z[f"W{i}"]), torch.from_numpy(z[f"b{i}"])) for i in range(2)]
+    loss, emb, grads = O.train_step(rowptr, col, X, weights, torch.from_numpy(z["mask"]), dtype=torch.float64)
+    assert abs(float(loss) - float(z["loss64"])) < 1e-10
+    assert np.allclose(emb.numpy(), z["z64"], atol=1e-10)
+    assert np.allclose(grads[0][0].numpy(), z["gW0_64"], atol=1e-10)
+    # fp32 oracle stays within the parity tolerance of the fp64 one
+    assert abs(float(z["loss32"]) - float(z["loss64"])) < 1e-5 * abs(float(z["loss64"]))
+
+
+def test_train_loss_decreases_on_zinc_like_batch():
+    # pin (6), qualitative: the epoch-mean loss of zinc250k.png starts ~1.1 and falls below 1.0;
+    # a fresh model starts higher and must descend towards that band
+    from gae_dgl_b200.synthetic import zinc_like_dataset
+    ds = zinc_like_dataset(64, seed=0)
+    graphs = [(*(g.edges()), g.number_of_nodes()) for g in ds]
+    s, d, n = O.batch_graphs(graphs)
+    rowptr, col = O.coo_to_csr(s, d, n)
+    X = torch.cat([g.ndata["h"] for g in ds])
+    torch.manual_seed(0)
+    model = O.OracleGAE(39, [32, 16])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    adj = O.dense_adj(s, d, n)
+    pw = O.pos_weight_inductive(adj)
+    losses = []
+    for _ in range(150):
+        loss = O.bce_loss(model(rowptr, col, X), adj, pw)
+        opt.zero_grad(); loss.backward(); opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] and losses[-1] < 1.3

@@ -1,0 +1,352 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (north_star): indexing bit-exact; embeddings and reconstruction loss within 1e-5
+relative fp32.  Parity norm: max|delta| / max(max|ref_fp64|, 1) per
+tensor, plus relative error of the scalar loss.  The oracle is evaluated in fp64.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gae_dgl_b200 as G
+from gae_dgl_b200 import _lib, ops, synthetic
+from oracle import gae_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "gae_small.npz")
+
+
+def rel_err(a, ref):
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    return float((a - ref).abs().max() / max(float(ref.abs().max()), 1.0))
+
+
+def random_graph(n, e, seed, hub=None):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, n, (e,), generator=g)
+    if hub:  # one very long row + an empty tail of rows
+        src = torch.cat([src, torch.randint(0, n, (hub,), generator=g)])
+        dst = torch.cat([dst, torch.full((hub,), 7)])
+    keep = dst < n - 5                      # last 5 rows empty
+    return src[keep], dst[keep]
+
+
+def to_dev(rowptr, col, cuda):
+    return rowptr.to(cuda), col.to(cuda)
+
+
+@pytest.mark.parametrize("d", [1, 3, 16, 32, 39, 64, 100, 128, 500, 1433])
+@pytest.mark.parametrize("rows_per_warp", [1, 2])
+def test_spmm_parity(cuda, d, rows_per_warp):
+    n = 700
+    src, dst = random_graph(n, 6000, seed=d, hub=3000)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(d + 1))
+    ref = O.spmm_sum(rowptr, col, X.double())
+    rp, cl = to_dev(rowptr, col, cuda)
+    _lib.set_tuning("spmm_rows_per_warp", rows_per_warp)
+    try:
+        for seg_len in (None, 512, 64):
+            plan = ops.build_hub_plan(rp, seg_len) if seg_len else None
+            if seg_len:
+                assert plan.n_long >= 1
+            for unroll in (4, 8):
+                _lib.set_tuning("spmm_unroll", unroll)
+                Y = ops.spmm(rp, cl, X.to(cuda), plan)
+                assert rel_err(Y, ref) < TOL, (d, seg_len, unroll)
+                assert float(Y[n - 5:].abs().max()) == 0.0          # empty rows are zeros
+    finally:
+        _lib.set_tuning("spmm_rows_per_warp", 1)
+        _lib.set_tuning("spmm_unroll", 8)
+
+
+@pytest.mark.parametrize("cache", [0, 1, 2])
+def test_spmm_cache_variants_bit_identical(cuda, cache):
+    n = 3000
+    src, dst = random_graph(n, 40000, seed=9, hub=5000)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    rp, cl = to_dev(rowptr, col, cuda)
+    X = torch.randn(n, 64, generator=torch.Generator().manual_seed(2)).to(cuda)
+    plan = ops.build_hub_plan(rp, 512)
+    base = ops.spmm(rp, cl, X, plan)
+    _lib.set_tuning("spmm_cache", cache)
+    try:
+        Y = ops.spmm(rp, cl, X, plan)
+    finally:
+        _lib.set_tuning("spmm_cache", 0)
+    assert torch.equal(Y, base)               # same summation order -> same bits
+    assert torch.equal(ops.spmm(rp, cl, X, plan), base)   # run-to-run deterministic
+
+
+def test_spmm_weighted_accumulate_and_unaligned(cuda):
+    n = 400
+    src, dst = random_graph(n, 5000, seed=4)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    rp, cl = to_dev(rowptr, col, cuda)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(n, 24, generator=g)
+    w = torch.rand(col.numel(), generator=g)
+    ref = O.spmm_sum(rowptr, col, X.double(), w.double())
+    Y = ops.spmm(rp, cl, X.to(cuda), vals=w.to(cuda))
+    assert rel_err(Y, ref) < TOL
+    Y0 = torch.randn(n, 24, generator=g)
+    out = Y0.to(cuda).clone()
+    ops.spmm(rp, cl, X.to(cuda), out=out, accumulate=True)
+    assert rel_err(out, Y0.double() + O.spmm_sum(rowptr, col, X.double())) < TOL
+    # scalar fallback: leading dimension not a multiple of 4, called through the raw C ABI
+    import ctypes
+    Xu = torch.zeros(n, 27, device=cuda)
+    Xu[:, :24] = X.to(cuda)
+    Yu = torch.zeros(n, 25, device=cuda)
+    rc = _lib.load().gae_spmm_csr_f32(rp.data_ptr(), cl.data_ptr(), None, Xu.data_ptr(), 27, Yu.data_ptr(), 25, n, 24,
+                                      None, None, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert rel_err(Yu[:, :24], O.spmm_sum(rowptr, col, X.double())) < TOL
+
+
+def test_spmm_empty_and_degenerate(cuda):
+    rp = torch.zeros(6, dtype=torch.int64, device=cuda)
+    cl = torch.zeros(0, dtype=torch.int32, device=cuda)
+    Y = ops.spmm(rp, cl, torch.randn(5, 16, device=cuda))
+    assert Y.shape == (5, 16) and float(Y.abs().max()) == 0.0
+    rp1 = torch.tensor([0, 3], dtype=torch.int64, device=cuda)      # single row, self loops
+    cl1 = torch.tensor([0, 0, 0], dtype=torch.int32, device=cuda)
+    X = torch.arange(4, dtype=torch.float32, device=cuda).reshape(1, 4)
+    assert torch.equal(ops.spmm(rp1, cl1, X), 3 * X)
+    lib = _lib.load()
+    assert lib.gae_spmm_csr_f32(None, None, None, None, 4, None, 4, 5, 4, None, None, 0, None) == -1
+    assert b"non-null" in lib.gae_last_error_string()
+
+
+def test_spmm_large_properties(cuda):
+    """Size-independent properties at a size the oracle would not finish quickly:
+    ones -> in-degrees (exact), linearity, adjoint identity <Y, A X> = <A^T Y, X>."""
+    scale, e = 18, 6_000_000
+    n = 1 << scale
+    src, dst = synthetic.rmat_edges(scale, e, seed=3, device=cuda)
+    g = G.DGLGraph.from_csr(*G.graph.coo_to_csr_torch(src, dst, n))
+    c, t = g.csr(), g.csr_t()
+    assert c.plan.n_long > 0                     # RMAT has hub rows
+    deg = g.in_degrees()
+    ones = torch.ones(n, 64, device=cuda)
+    Y1 = ops.spmm(c.rowptr, c.col, ones, c.plan)
+    assert torch.equal(Y1[:, 0], deg.float()) and torch.equal(Y1[:, 63], deg.float())   # exact: small integers
+    assert int(deg.sum()) == e
+    X = synthetic.hashed_normal(n, 64, 5, device=cuda)
+    Z = synthetic.hashed_normal(n, 64, 6, device=cuda)
+    YX, YZ = ops.spmm(c.rowptr, c.col, X, c.plan), ops.spmm(c.rowptr, c.col, Z, c.plan)
+    Ysum = ops.spmm(c.rowptr, c.col, X + 2 * Z, c.plan)
+    assert rel_err(Ysum, YX.double() + 2 * YZ.double()) < TOL
+    lhs = (Z.double() * YX.double()).sum()
+    rhs = (ops.spmm(t.rowptr, t.col, Z, t.plan).double() * X.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-6 * abs(float(lhs)) + 1e-3
+    # C oracle on the same graph (seconds on the host)
+    from oracle import c_spmm
+    ref = c_spmm.spmm_f64acc(c.rowptr.cpu().numpy(), c.col.cpu().numpy(), X.cpu().numpy())
+    assert rel_err(YX, torch.from_numpy(ref)) < TOL
+
+
+@pytest.mark.parametrize("n,d_in,d_out,act", [(300, 39, 32, 1), (300, 32, 16, 0), (1000, 500, 32, 1),
+                                                (257, 1433, 32, 1), (5, 7, 3, 1), (70000, 64, 32, 1)])
+def test_linear_fwd_bwd_parity(cuda, n, d_in, d_out, act):
+    g = torch.Generator().manual_seed(n + d_in)
+    Y = torch.randn(n, d_in, generator=g)
+    W = torch.randn(d_out, d_in, generator=g) / d_in ** 0.5
+    b = torch.randn(d_out, generator=g)
+    dH = torch.randn(n, d_out, generator=g)
+    Yr, Wr, br = (t.double().requires_grad_(True) for t in (Y, W, b))
+    pre = Yr @ Wr.t() + br
+    Hr = torch.relu(pre) if act else pre
+    Hr.backward(dH.double())
+    Yc, Wc, bc = (t.to(cuda).requires_grad_(True) for t in (Y, W, b))
+    H = ops.LinearActFunction.apply(Yc, Wc, bc, act)
+    H.backward(dH.to(cuda))
+    assert rel_err(H, Hr) < TOL
+    assert rel_err(Yc.grad, Yr.grad) < TOL
+    assert rel_err(Wc.grad, Wr.grad) < TOL
+    assert rel_err(bc.grad, br.grad) < TOL
+
+
+def test_dropout_mask_injection_and_philox(cuda):
+    Z = torch.randn(1000, 16, device=cuda)
+    mask = (torch.rand(1000, 16) >= 0.1)
+    Zd, m = ops.dropout_fwd(Z, 0.1, mask)
+    assert torch.equal(Zd.cpu(), O.apply_dropout_mask(Z.cpu(), mask, 0.1))
+    Zd2, m2 = ops.dropout_fwd(Z, 0.1, None, seed=123, offset=5)
+    keep = m2.float().mean().item()
+    assert 0.88 < keep < 0.92                                     # pin (1): ~10 % dropped
+    kept = m2.bool()
+    assert torch.allclose(Zd2[kept], Z[kept] / 0.9) and float(Zd2[~kept].abs().max()) == 0.0
+    Zd3, m3 = ops.dropout_fwd(Z, 0.1, None, seed=123, offset=5)
+    assert torch.equal(m2, m3)                                    # counter-based: reproducible
+    _, m4 = ops.dropout_fwd(Z, 0.1, None, seed=124, offset=5)
+    assert not torch.equal(m2, m4)
+    dZ = ops.dropout_bwd(torch.ones_like(Z), m2, 0.1, grad_scale=torch.tensor(2.0))
+    assert torch.allclose(dZ, m2.float() * (2.0 / 0.9))
+
+
+@pytest.mark.parametrize("n,d,e", [(50, 16, 120), (700, 16, 3000), (1500, 16, 4000), (300, 32, 900), (200, 48, 700),
+                                    (130, 5, 300)])
+def test_decoder_loss_and_grad_parity(cuda, n, d, e):
+    src, dst = random_graph(n, e, seed=n)
+    src = torch.cat([src, src[:20]])
+    dst = torch.cat([dst, dst[:20]])                    # duplicate edges: y = 2
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    rt, ct = O.csr_transpose(rowptr, col)
+    adj = O.dense_adj(src, dst, n, torch.float64)
+    pw = float(O.pos_weight_inductive(adj.float()))
+    g = torch.Generator().manual_seed(e)
+    Z = 0.5 * torch.randn(n, d, generator=g)
+    Zr = Z.double().requires_grad_(True)
+    ref = O.bce_loss(Zr @ Zr.t(), adj, torch.tensor(pw, dtype=torch.float64))
+    ref.backward()
+    loss, dZ = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), pw,
+                               want_loss=True, want_grad=True)
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    scale = float(Zr.grad.abs().max())
+    assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * scale
+    loss_only, none = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), None, None, pw, True, False)
+    assert none is None and float(loss_only) == float(loss)
+    X = ops.decoder_logits(Z.to(cuda))
+    assert rel_err(X, Z.double() @ Z.double().t()) < TOL
+
+
+def _load_weights(model, weights):
+    with torch.no_grad():
+        for layer, (W, b) in zip(model.layers, weights):
+            layer.apply_mod.linear.weight.copy_(W)
+            layer.apply_mod.linear.bias.copy_(b)
+
+
+def _check_step(cuda, g, X, weights, mask, transductive=False):
+    """One training step through the public module surface vs the oracle in fp64."""
+    rowptr, col = g.csr().rowptr.cpu(), g.csr().col.cpu()
+    loss_ref, z_ref, grads_ref = O.train_step(rowptr, col, X, weights, mask, p=0.1, transductive=transductive,
+                                              dtype=torch.float64)
+    model = G.GAE(X.shape[1], [w[0].shape[0] for w in weights])
+    _load_weights(model, weights)
+    model.to(cuda)
+    g.to(cuda)
+    g.ndata["h"] = X.to(cuda)
+    loss = model.loss(g, mask=mask.to(cuda), transductive=transductive)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    assert rel_err(g.ndata["h"], z_ref) < TOL                       # gae.py:53 write-back = embeddings
+    for layer, (gW, gb) in zip(model.layers, grads_ref):
+        lin = layer.apply_mod.linear
+        assert float((lin.weight.grad.double().cpu() - gW).abs().max()) < TOL * max(float(gW.abs().max()), 1e-30) * 5
+        assert float((lin.bias.grad.double().cpu() - gb).abs().max()) < TOL * max(float(gb.abs().max()), 1e-30) * 5
+    return float(loss), model
+
+
+def test_train_step_parity_golden(cuda):
+    z = np.load(GOLDEN)
+    g = G.DGLGraph((z["src"], z["dst"], int(z["n"])))
+    assert np.array_equal(g.csr().rowptr.numpy(), z["rowptr"]) and np.array_equal(g.csr().col.numpy(), z["col"])
+    X = torch.from_numpy(z["X"])
+    weights = [(torch.from_numpy(z[f"W{i}"]), torch.from_numpy(z[f"b{i}"])) for i in range(2)]
+    assert G.pos_weight_of(g) == float(z["pos_weight"])
+    loss, model = _check_step(cuda, g, X, weights, torch.from_numpy(z["mask"]))
+    assert abs(loss - float(z["loss64"])) < TOL * abs(float(z["loss64"]))
+    # forward(g) compatibility path returns the dense logits of the reference
+    g.ndata["h"] = X.to(cuda)
+    logits = model.decoder(model.encode(g), mask=torch.from_numpy(z["mask"]).to(cuda))
+    zd = O.apply_dropout_mask(torch.from_numpy(z["z64"]), torch.from_numpy(z["mask"]), 0.1)
+    assert rel_err(logits, zd @ zd.t()) < TOL
+    spm = ops.spmm(g.csr().rowptr, g.csr().col, X.to(cuda), g.csr().plan)
+    assert rel_err(spm, torch.from_numpy(z["spmm64"])) < TOL
+
+
+def test_train_step_parity_cora_like(cuda):
+    g, X = synthetic.planetoid_like("cora", seed=0)
+    torch.manual_seed(1)
+    ref = O.OracleGAE(1433, [32, 16])
+    weights = [(l.apply_mod.linear.weight.detach(), l.apply_mod.linear.bias.detach()) for l in ref.layers]
+    mask = torch.rand(2708, 16) >= 0.1
+    _check_step(cuda, g, X, weights, mask, transductive=True)
+
+
+def test_train_step_parity_zinc_batch(cuda):
+    ds = synthetic.zinc_like_dataset(128, seed=1)
+    bg = G.batch(ds, device=cuda)                       # device collation path (gae_batch_offset_cols_i32)
+    s, d, n = O.batch_graphs([(*g.edges(), g.number_of_nodes()) for g in ds])
+    rp, col = O.coo_to_csr(s, d, n)
+    assert torch.equal(bg.csr().rowptr.cpu(), rp) and torch.equal(bg.csr().col.cpu(), col)      # bit-exact indexing
+    rt, ct = O.csr_transpose(rp, col)
+    assert torch.equal(bg.csr_t().rowptr.cpu(), rt) and torch.equal(bg.csr_t().col.cpu(), ct)
+    assert torch.equal(bg.in_degrees().cpu(), O.in_degrees(rp))
+    X = bg.ndata["h"].cpu()
+    torch.manual_seed(2)
+    ref = O.OracleGAE(39, [32, 16])
+    weights = [(l.apply_mod.linear.weight.detach(), l.apply_mod.linear.bias.detach()) for l in ref.layers]
+    mask = torch.rand(n, 16) >= 0.1
+    _check_step(cuda, bg, X, weights, mask)
+
+
+def test_dense_reference_formulation_matches_fused(cuda):
+    """train_inductive.py:44-48 executed literally (dense adj, forward(g), torch BCE) gives the
+    same loss and gradients as the fused path."""
+    ds = synthetic.zinc_like_dataset(16, seed=5)
+    bg = G.batch(ds, device=cuda)
+    X = bg.ndata["h"].clone()
+    n = bg.number_of_nodes()
+    mask = (torch.rand(n, 16) >= 0.1).to(cuda)
+    torch.manual_seed(3)
+    model = G.GAE(39, [32, 16]).to(cuda)
+    loss_f = model.loss(bg, mask=mask)
+    loss_f.backward()
+    gf = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    bg.ndata["h"] = X
+    adj = bg.adjacency_matrix().to_dense()
+    pw = (adj.shape[0] * adj.shape[0] - adj.sum()) / adj.sum()
+    h = model.encode(bg)
+    logits = model.decoder(h, mask=mask)
+    loss_d = torch.nn.functional.binary_cross_entropy_with_logits(logits, adj, pos_weight=pw)
+    loss_d.backward()
+    assert abs(float(loss_f) - float(loss_d)) < TOL * abs(float(loss_d))
+    for a, p in zip(gf, model.parameters()):
+        assert float((a - p.grad).abs().max()) < 2e-5 * max(float(p.grad.abs().max()), 1e-30)
+
+
+def test_vgae_and_single_layer(cuda):
+    g, X = synthetic.planetoid_like("cora", seed=1)
+    g.to(cuda)
+    torch.manual_seed(0)
+    v = G.VGAE(1433, [32, 16]).to(cuda)
+    g.ndata["h"] = X.to(cuda)
+    mu, logstd = v.encode_dist(g)
+    eps = torch.randn_like(mu)
+    mask = (torch.rand(2708, 16) >= 0.1).to(cuda)
+    g.ndata["h"] = X.to(cuda)
+    loss = v.loss(g, mask=mask, eps=eps)
+    loss.backward()
+    assert torch.isfinite(loss) and v.mu_head.apply_mod.linear.weight.grad.abs().sum() > 0
+    kl_ref = O.vgae_kl(mu.detach().double().cpu(), logstd.detach().double().cpu())
+    assert abs(float(v.kl(mu, logstd)) - float(kl_ref)) < 1e-5 * max(abs(float(kl_ref)), 1.0)
+    one = G.GAE(1433, [16]).to(cuda)
+    g.ndata["h"] = X.to(cuda)
+    z = one.encode(g)
+    rowptr, col = g.csr().rowptr.cpu(), g.csr().col.cpu()
+    lin = one.layers[0].apply_mod.linear
+    ref = O.encode(rowptr, col, X.double(), [(lin.weight.detach().double().cpu(), lin.bias.detach().double().cpu())])
+    assert rel_err(z, ref) < TOL
+
+
+def test_trainers_run_and_learn(cuda, tmp_path):
+    from gae_dgl_b200 import train_inductive, train_transductive
+    tl, vl = train_inductive.main(["--synthetic", "600", "--n_epochs", "3", "--batch_size", "64", "--lr", "0.01",
+                                   "--save_dir", str(tmp_path), "--seed", "0", "--hidden_dims", "32", "16"])
+    assert tl[-1] < tl[0] and os.path.exists(tmp_path / "ep02.pkl")
+    sd = torch.load(tmp_path / "ep02.pkl")
+    O.OracleGAE(39, [32, 16]).load_state_dict(sd)              # checkpoint loads into the reference-shaped module
+    tl2, _ = train_inductive.main(["--synthetic", "600", "--n_epochs", "4", "--batch_size", "64", "--lr", "0.01",
+                                   "--save_dir", str(tmp_path), "--seed", "0", "--resume", str(tmp_path / "ep02.ckpt")])
+    assert len(tl2) == 1
+    losses = train_transductive.main(["--dataset", "cora", "--n_epochs", "30", "--save_dir", str(tmp_path), "--seed", "0"])
+    assert losses[-1] < losses[0]
