@@ -390,10 +390,10 @@ def run_ours(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     fwd_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]
     bwd_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
-    t = torch.tensor([total_ms, statistics.mean(fwd_ms), statistics.mean(bwd_ms)], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([total_ms, statistics.mean(fwd_ms), statistics.mean(bwd_ms)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fwd_mean, bwd_mean = (float(x) for x in t)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, fwd_mean, bwd_mean = (float(x) for x in tmax)
     ms_per_step = total_ms / args.steps
     value = total_edges / (ms_per_step * 1e-3)
 

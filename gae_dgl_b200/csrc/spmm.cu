@@ -260,7 +260,7 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     const bool vec = aligned16(X) && aligned16(Y) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                      (!use_plan || aligned16(partial_ws));
     int block = tuning(T_SPMM_BLOCK);
-    if (block != 128 && block != 256 && block != 512) block = 256;
+    if (block != 32 && block != 64 && block != 128 && block != 256 && block != 512) block = 128;
     const int unroll = tuning(T_SPMM_UNROLL);
     const int cache = tuning(T_SPMM_CACHE);
     const int rpw = tuning(T_SPMM_ROWS_PER_WARP);

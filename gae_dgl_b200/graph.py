@@ -95,15 +95,17 @@ def coo_to_csr_numpy(src: np.ndarray, dst: np.ndarray, n: int):
     return rowptr, col
 
 
-def coo_to_csr_torch(src: torch.Tensor, dst: torch.Tensor, n: int):
+def coo_to_csr_torch(src: torch.Tensor, dst: torch.Tensor, n: int, n_cols: Optional[int] = None):
     """Same on whatever device the int64 edge tensors live on (used for the 1e8-edge RMAT
-    graphs, which are generated and sorted on the GPU)."""
+    graphs, which are generated and sorted on the GPU).  `n` rows; column ids < n_cols
+    (default n) -- rectangular for the [local | halo] column space of a vertex partition."""
+    m = n if n_cols is None else n_cols
     if src.numel() == 0:
         return torch.zeros(n + 1, dtype=torch.int64, device=src.device), torch.zeros(0, dtype=torch.int32, device=src.device)
-    key = dst * n + src
+    key = dst * m + src
     key, _ = torch.sort(key)
-    col = (key % n).to(torch.int32)
-    rows = torch.div(key, n, rounding_mode="floor")
+    col = (key % m).to(torch.int32)
+    rows = torch.div(key, m, rounding_mode="floor")
     del key
     rowptr = torch.zeros(n + 1, dtype=torch.int64, device=src.device)
     rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--no-permute", action="store_true")
     ap.add_argument("--seg-lens", type=str, default="512")
     ap.add_argument("--tune", type=str, default="")
+    ap.add_argument("--blocks", type=str, default="32,64,128,256")
+    ap.add_argument("--caches", type=str, default="0,1")
     ap.add_argument("--out", type=str, default="")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -61,6 +63,8 @@ def main():
         return e0.elapsed_time(e1) / iters
 
     results = []
+    blocks = [int(b) for b in args.blocks.split(',')]
+    caches = [int(b) for b in args.caches.split(',')]
     seg_lens = [int(s) for s in args.seg_lens.split(",")]
     if not args.sweep:
         plan = ops.build_hub_plan(rowptr, seg_lens[0])
@@ -72,7 +76,7 @@ def main():
     for seg in seg_lens:
         plan = ops.build_hub_plan(rowptr, seg)
         ws = plan.workspace(args.d, dev)
-        for block, unroll, cache, rpw in itertools.product((128, 256, 512), (4, 8), (0, 1, 2), (1, 2)):
+        for block, unroll, cache, rpw in itertools.product(blocks, (4, 8), caches, (1, 2)):
             _lib.set_tuning("spmm_block", block)
             _lib.set_tuning("spmm_unroll", unroll)
             _lib.set_tuning("spmm_cache", cache)
