@@ -9,11 +9,12 @@ namespace gae {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-// defaults (B200 sweeps, profiles/r01_sweep_*.json): 8 gathers in flight, 64-thread CTAs, plain
-// caching, half-warp per row for rows <= seg_len (hub rows always use whole warps per segment)
-static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {8}, {64}, {0}, {2}, {0}};
+// defaults (B200 sweeps, profiles/r01_sweep_*.json): register-gather variant, 4 gathers in flight per
+// lane at 40 registers (48 warps/SM), 64-thread CTAs, plain caching, warp per row
+static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {4}, {64}, {0}, {1}, {0}, {2}};
 static const char *const g_tuning_names[T_COUNT] = {"spmm_variant", "spmm_unroll", "spmm_block",
-                                                     "spmm_cache", "spmm_rows_per_warp", "dec_splits"};
+                                                     "spmm_cache", "spmm_rows_per_warp", "dec_splits",
+                                                     "spmm_stages"};
 
 void set_error(const char *fmt, ...) {
     va_list ap;

@@ -13,12 +13,13 @@ void count_launch(int n = 1);
 int32_t tuning(int idx);
 
 enum TuningIdx {
-    T_SPMM_VARIANT = 0,  // 0 = LDG warp-per-row, 1 = bulk-async (cp.async.bulk) staged rows
+    T_SPMM_VARIANT = 0,  // 0 = register gather (LDG.128), 1 = streaming + cp.async.bulk (TMA), 2 = streaming + LDGSTS
     T_SPMM_UNROLL,       // gathers in flight per lane group (4 / 8 / 16)
     T_SPMM_BLOCK,        // threads per CTA (128 / 256 / 512)
     T_SPMM_CACHE,        // 0 = plain ld.global.nc ; 1 = X evict_last + streaming idx/Y
     T_SPMM_ROWS_PER_WARP,// 1 = warp per row, 2 = half-warp per row (d <= 64)
     T_DEC_SPLITS,        // 0 = auto
+    T_SPMM_STAGES,       // streaming variant: batches of 32 rows in flight per warp (2/3/4)
     T_COUNT
 };
 
@@ -50,6 +51,22 @@ enum TuningIdx {
         }                                                                                \
         gae::count_launch();                                                             \
     } while (0)
+
+// arguments of the streaming SpMM variant (spmm_stream.cu)
+struct StreamArgs {
+    const int64_t *rowptr;
+    const int32_t *col;
+    const float *X;
+    int64_t ldx;
+    float *Y;          // rows pass: Y ; segment pass: partial buffer
+    int64_t ldy;
+    int64_t n_items;
+    int32_t seg_len;   // rows pass: skip rows with deg > seg_len (0 = never)
+    int32_t accumulate;
+    const int32_t *long_row;
+    const int64_t *long_seg_ptr;
+    const int32_t *seg_row;
+};
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -67,8 +67,9 @@ __device__ __forceinline__ int ld_idx(const int32_t *p) {
 }
 
 // LPR lanes per feature row, GPR groups per dst row, U gathers in flight per lane.
-template <int LPR, int GPR, int U, bool VALS, int CACHE, bool SEG>
-__global__ void __launch_bounds__(512, 1) spmm_vec_kernel(const SpmmArgs a) {
+// MINB: resident 128-thread CTAs per SM the register allocation must allow (occupancy target).
+template <int LPR, int GPR, int U, bool VALS, int CACHE, bool SEG, int MINB>
+__global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
     constexpr int G = 32 / LPR;
     constexpr int RPW = G / GPR;
     static_assert(G % GPR == 0, "GPR must divide G");
@@ -117,22 +118,26 @@ __global__ void __launch_bounds__(512, 1) spmm_vec_kernel(const SpmmArgs a) {
         // Loads are UNCONDITIONAL (edge index clamped to the row's last edge, which re-hits a
         // line already in flight) so the compiler keeps all U index loads and then all U row
         // gathers in flight; only the adds are predicated.
-        const int64_t last = end - 1;
-        for (int64_t e = start + phase; e < end; e += (int64_t)GPR * U) {
+        // 32-bit edge offsets inside the row keep the loop control to a few integer ops
+        const int len = (int)(end - start);
+        const int32_t *cp = a.col + start;
+        const float *wp = VALS ? a.vals + start : nullptr;
+        const int ldx = (int)a.ldx;
+        for (int i = phase; i < len; i += GPR * U) {
             int c[U];
             float w[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int64_t ee = min(e + (int64_t)u * GPR, last);
-                c[u] = ld_idx(a.col + ee);
-                if (VALS) w[u] = __ldg(a.vals + ee);
+                const int ii = min(i + u * GPR, len - 1);
+                c[u] = ld_idx(cp + ii);
+                if (VALS) w[u] = __ldg(wp + ii);
             }
             float4 v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = gather_f4<CACHE>(xb + (int64_t)c[u] * a.ldx, pol);
+            for (int u = 0; u < U; ++u) v[u] = gather_f4<CACHE>(xb + (int64_t)c[u] * ldx, pol);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (e + (int64_t)u * GPR < end) {
+                if (i + u * GPR < len) {
                     if (VALS) f4_fma(acc, w[u], v[u]);
                     else f4_add(acc, v[u]);
                 }
@@ -196,11 +201,13 @@ __global__ void spmm_scalar_kernel(const SpmmArgs a) {
 template <int LPR, int GPR, int U, bool VALS, int CACHE, bool SEG>
 static cudaError_t launch_one(const SpmmArgs &a, int block, cudaStream_t st) {
     constexpr int RPW = (32 / LPR) / GPR;
+    // occupancy target: U=4 fits 40 registers (12 CTAs of 128 threads), U=8 needs 64 (8 CTAs)
+    constexpr int MINB = (U <= 2) ? 16 : (U <= 4) ? 12 : 8;
     const int wpb = block / 32;
     const int64_t warps = cdiv(a.n_items, RPW);
     const int64_t blocks = cdiv(warps, wpb);
     if (blocks == 0) return cudaSuccess;
-    spmm_vec_kernel<LPR, GPR, U, VALS, CACHE, SEG><<<(unsigned)blocks, block, 0, st>>>(a);
+    spmm_vec_kernel<LPR, GPR, U, VALS, CACHE, SEG, MINB><<<(unsigned)blocks, block, 0, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }
@@ -212,11 +219,8 @@ static cudaError_t launch_shape(const SpmmArgs &a, int unroll, int cache, int bl
         if (unroll >= 8) return launch_one<LPR, GPR, 8, false, 1, SEG>(a, block, st);
         return launch_one<LPR, GPR, 4, false, 1, SEG>(a, block, st);
     }
-    if (cache == 2) {
-        if (unroll >= 8) return launch_one<LPR, GPR, 8, false, 2, SEG>(a, block, st);
-        return launch_one<LPR, GPR, 4, false, 2, SEG>(a, block, st);
-    }
     if (unroll >= 8) return launch_one<LPR, GPR, 8, false, 0, SEG>(a, block, st);
+    if (unroll <= 2) return launch_one<LPR, GPR, 2, false, 0, SEG>(a, block, st);
     return launch_one<LPR, GPR, 4, false, 0, SEG>(a, block, st);
 }
 
@@ -234,6 +238,8 @@ static cudaError_t launch_vec(const SpmmArgs &a, int rows_per_warp, int unroll, 
     return launch_shape<32, 1, SEG>(a, unroll, cache, block, st);
 }
 
+cudaError_t spmm_stream_launch(const StreamArgs &a, int d, bool seg, int stages, int mode, cudaStream_t st);
+
 }  // namespace gae
 
 using namespace gae;
@@ -246,6 +252,7 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     if (n_rows == 0 || d == 0) return GAE_OK;
     GAE_CHECK_ARG(rowptr && X && Y, "rowptr, X, Y must be non-null");
     GAE_CHECK_ARG(ldx >= d && ldy >= d, "leading dimensions must be >= d");
+    GAE_CHECK_ARG(ldx < (int64_t)1 << 31, "ldx must fit in 31 bits");
     cudaStream_t st = (cudaStream_t)stream;
     const bool use_plan = plan && plan->n_seg > 0;
     if (use_plan) {
@@ -260,7 +267,7 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     const bool vec = aligned16(X) && aligned16(Y) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                      (!use_plan || aligned16(partial_ws));
     int block = tuning(T_SPMM_BLOCK);
-    if (block != 32 && block != 64 && block != 128 && block != 256 && block != 512) block = 128;
+    if (block != 32 && block != 64 && block != 128) block = 64;
     const int unroll = tuning(T_SPMM_UNROLL);
     const int cache = tuning(T_SPMM_CACHE);
     const int rpw = tuning(T_SPMM_ROWS_PER_WARP);
@@ -271,6 +278,28 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
         const int64_t blocks = cdiv(n_rows, block / 32);
         spmm_scalar_kernel<<<(unsigned)blocks, block, 0, st>>>(a);
         GAE_LAUNCH_CHECK();
+        return GAE_OK;
+    }
+    const int variant = tuning(T_SPMM_VARIANT);
+    const bool stream_ok = (variant == 1 || variant == 2) && !vals && (d == 32 || d == 64 || d == 128) &&
+                           ldy % 4 == 0;
+    if (stream_ok) {
+        // streaming variant: bulk-async staged gather, sequential segmented sum (spmm_stream.cu)
+        StreamArgs sa{};
+        sa.rowptr = rowptr; sa.col = col; sa.X = X; sa.ldx = ldx; sa.Y = Y; sa.ldy = ldy; sa.n_items = n_rows;
+        sa.seg_len = a.seg_len; sa.accumulate = accumulate;
+        const int stages = tuning(T_SPMM_STAGES);
+        GAE_CUDA(spmm_stream_launch(sa, d, false, stages, variant - 1, st));
+        if (use_plan) {
+            StreamArgs ss = sa;
+            ss.Y = partial_ws; ss.ldy = d; ss.n_items = plan->n_seg; ss.seg_len = plan->seg_len; ss.accumulate = 0;
+            ss.long_row = plan->long_row; ss.long_seg_ptr = plan->long_seg_ptr; ss.seg_row = plan->seg_row;
+            GAE_CUDA(spmm_stream_launch(ss, d, true, stages, variant - 1, st));
+            const int64_t threads = plan->n_long * (d / 4);
+            spmm_hub_reduce_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(
+                partial_ws, d, plan->long_row, plan->long_seg_ptr, plan->n_long, Y, ldy, d, accumulate);
+            GAE_LAUNCH_CHECK();
+        }
         return GAE_OK;
     }
     GAE_CUDA(launch_vec<false>(a, rpw, unroll, cache, block, st));

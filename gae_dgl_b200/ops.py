@@ -20,7 +20,7 @@ ACT_IDENTITY = 0
 ACT_RELU = 1
 DEC_LOSS = 1
 DEC_GRAD = 2
-DEFAULT_SEG_LEN = 128
+DEFAULT_SEG_LEN = 256
 
 
 # ------------------------------------------------------------------------------------------

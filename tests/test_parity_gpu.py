@@ -83,6 +83,47 @@ def test_spmm_cache_variants_bit_identical(cuda, cache):
     assert torch.equal(ops.spmm(rp, cl, X, plan), base)   # run-to-run deterministic
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spmm_stream_variants(cuda, variant, d):
+    """Streaming variants (cp.async.bulk / LDGSTS staged gather): parity, and -- because the row
+    sum runs sequentially in CSR order -- BIT-exact agreement with the oracle's sequential fp32
+    loop for every row that is not split into hub segments."""
+    from oracle import c_spmm
+    n = 5000
+    src, dst = random_graph(n, 60000, seed=d + variant, hub=4000)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(d))
+    ref64 = O.spmm_sum(rowptr, col, X.double())
+    seq32 = torch.from_numpy(c_spmm.spmm_f32(rowptr.numpy(), col.numpy(), X.numpy()))
+    rp, cl = to_dev(rowptr, col, cuda)
+    deg = rowptr[1:] - rowptr[:-1]
+    _lib.set_tuning("spmm_variant", variant)
+    try:
+        for stages in (2, 3, 4):
+            _lib.set_tuning("spmm_stages", stages)
+            for seg_len in (None, 128, 33):
+                plan = ops.build_hub_plan(rp, seg_len) if seg_len else None
+                Y = ops.spmm(rp, cl, X.to(cuda), plan)
+                assert rel_err(Y, ref64) < TOL, (variant, d, stages, seg_len)
+                whole = deg <= (seg_len or 10 ** 9)
+                assert torch.equal(Y.cpu()[whole], seq32[whole]), (variant, d, stages, seg_len)
+                assert float(Y[n - 5:].abs().max()) == 0.0
+        Y0 = torch.randn(n, d, generator=torch.Generator().manual_seed(5))
+        out = Y0.to(cuda).clone()
+        ops.spmm(rp, cl, X.to(cuda), ops.build_hub_plan(rp, 128), out=out, accumulate=True)
+        assert rel_err(out, Y0.double() + ref64) < TOL
+        # tiny and ragged row counts (n not a multiple of 32, all-empty warps)
+        rp2 = torch.tensor([0, 0, 2, 2, 5], dtype=torch.int64, device=cuda)
+        cl2 = torch.tensor([1, 3, 0, 0, 2], dtype=torch.int32, device=cuda)
+        X2 = torch.randn(4, d, device=cuda)
+        ref2 = O.spmm_sum(rp2.cpu(), cl2.cpu(), X2.cpu().double())
+        assert rel_err(ops.spmm(rp2, cl2, X2), ref2) < TOL
+    finally:
+        _lib.set_tuning("spmm_variant", 0)
+        _lib.set_tuning("spmm_stages", 3)
+
+
 def test_spmm_weighted_accumulate_and_unaligned(cuda):
     n = 400
     src, dst = random_graph(n, 5000, seed=4)

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torch.distributed.run): partitioned SpMM fwd/bwd with both
+exchange mechanisms vs the CPU oracle on the full graph."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device(f"cuda:{int(os.environ['LOCAL_RANK'])}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    from gae_dgl_b200 import parallel, synthetic
+    from oracle import c_spmm
+    from oracle import gae_oracle as O
+    scale, n_edges, d = 16, 2_000_000, 64
+    n = 1 << scale
+    ok = True
+    for exchange in ("nccl", "p2p"):
+        part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange)
+        Yf = part.fwd().clone()
+        Yb = part.bwd().clone()
+        torch.cuda.synchronize()
+        bounds = parallel.block_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        S, D = synthetic.rmat_edges(scale, n_edges, seed=1)
+        rp, col = O.coo_to_csr(S, D, n)
+        rpt, colt = O.coo_to_csr(D, S, n)
+        X = synthetic.hashed_normal(n, d, 2).numpy()
+        dY = synthetic.hashed_normal(n, d, 3).numpy()
+        ref_f = torch.from_numpy(c_spmm.spmm_f64acc(rp.numpy(), col.numpy(), X))[lo:hi]
+        ref_b = torch.from_numpy(c_spmm.spmm_f64acc(rpt.numpy(), colt.numpy(), dY))[lo:hi]
+        ef = float((Yf.double().cpu() - ref_f).abs().max() / max(float(ref_f.abs().max()), 1.0))
+        eb = float((Yb.double().cpu() - ref_b).abs().max() / max(float(ref_b.abs().max()), 1.0))
+        print(f"[rank {rank}] exchange={exchange} fwd_err={ef:.2e} bwd_err={eb:.2e} halo={part.halo_rows} "
+              f"local_rows={part.local_rows} local_edges={part.local_edges}", flush=True)
+        ok = ok and ef < 1e-5 and eb < 1e-5
+        del part
+        torch.cuda.empty_cache()
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if int(t) == 1 else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

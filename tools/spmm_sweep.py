@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--tune", type=str, default="")
     ap.add_argument("--blocks", type=str, default="32,64,128,256")
     ap.add_argument("--caches", type=str, default="0,1")
+    ap.add_argument("--variants", type=str, default="0")
+    ap.add_argument("--unrolls", type=str, default="4,8")
+    ap.add_argument("--stages", type=str, default="2,3,4")
     ap.add_argument("--out", type=str, default="")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -65,6 +68,7 @@ def main():
     results = []
     blocks = [int(b) for b in args.blocks.split(',')]
     caches = [int(b) for b in args.caches.split(',')]
+    unrolls = [int(b) for b in args.unrolls.split(',')]
     seg_lens = [int(s) for s in args.seg_lens.split(",")]
     if not args.sweep:
         plan = ops.build_hub_plan(rowptr, seg_lens[0])
@@ -76,7 +80,23 @@ def main():
     for seg in seg_lens:
         plan = ops.build_hub_plan(rowptr, seg)
         ws = plan.workspace(args.d, dev)
-        for block, unroll, cache, rpw in itertools.product(blocks, (4, 8), caches, (1, 2)):
+        for variant in [int(v) for v in args.variants.split(",")]:
+            if variant == 0:
+                continue
+            _lib.set_tuning("spmm_variant", variant)
+            for stages in [int(v) for v in args.stages.split(",")]:
+                _lib.set_tuning("spmm_stages", stages)
+                ms = timeit(plan, ws, args.iters)
+                if ref is None:
+                    ref = Y.clone()
+                r = {"seg_len": seg, "variant": variant, "stages": stages, "ms": ms, "alg_GBps": alg / ms / 1e6,
+                     "maxdiff_vs_first": float((Y - ref).abs().max())}
+                results.append(r)
+                print(json.dumps(r), flush=True)
+        _lib.set_tuning("spmm_variant", 0)
+        if "0" not in args.variants.split(","):
+            continue
+        for block, unroll, cache, rpw in itertools.product(blocks, unrolls, caches, (1, 2)):
             _lib.set_tuning("spmm_block", block)
             _lib.set_tuning("spmm_unroll", unroll)
             _lib.set_tuning("spmm_cache", cache)
