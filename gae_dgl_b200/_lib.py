@@ -50,6 +50,8 @@ SIGNATURES = {
                                    c_int32, c_void_p]),
     "gae_dropout_fwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float,
                                     c_uint64, c_uint64, c_int32, c_void_p]),
+    "gae_dropout_fwd_devrng_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float,
+                                           c_void_p, c_void_p]),
     "gae_dropout_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_float,
                                     c_void_p, c_void_p]),
     "gae_decoder_ws_bytes": (c_int64, [c_int64, c_int32]),
@@ -61,6 +63,8 @@ SIGNATURES = {
     "gae_gather_rows_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "gae_pull_rows_p2p_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64,
                                       c_void_p]),
+    "gae_push_rows_p2p_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                      c_int32, c_void_p]),
     "gae_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8 * 64), POINTER(c_int64)]),
     "gae_ipc_open_handle": (c_int, [POINTER(c_uint8 * 64), POINTER(c_void_p)]),
     "gae_ipc_close_handle": (c_int, [c_void_p]),

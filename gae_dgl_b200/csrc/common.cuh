@@ -120,10 +120,15 @@ __device__ __forceinline__ void st_stream_f4(float *p, const float4 &v) {
 //   e = exp(-|x|);  l = log(1+e);  softplus(x) = max(x,0) + l;  softplus(-x) = max(-x,0) + l;
 //   sigmoid(x) = x>=0 ? 1/(1+e) : e/(1+e)
 __device__ __forceinline__ void softplus_parts(float x, float &l, float &sg) {
-    const float e = __expf(-fabsf(x));
+    // raw MUFU ops (ex2 / rcp / lg2 .approx.ftz, each ~1 ulp): 1+e lies in (1,2], so none of the
+    // IEEE slow paths that __frcp_rn / expf / logf carry (a conditional CALL per pair) is needed
+    float e, r, l2;
+    const float t = -fabsf(x) * 1.4426950408889634f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
     const float one_e = 1.0f + e;
-    const float r = __frcp_rn(one_e);
-    l = __logf(one_e);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(one_e));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(one_e));
+    l = l2 * 0.6931471805599453f;
     sg = (x >= 0.f) ? r : e * r;
 }
 

@@ -37,9 +37,25 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     c->JT = 2048 / c->D;
     const int64_t rows_per_block = (int64_t)DEC_THREADS * c->R;
     c->nb = cdiv(n, rows_per_block);
-    int64_t want = tuning(T_DEC_SPLITS);
-    if (want <= 0) want = cdiv(148 * 6, c->nb);
     int64_t max_splits = cdiv(n, c->JT);
+    int64_t want = tuning(T_DEC_SPLITS);
+    if (want <= 0) {
+        // ~3 waves of CTAs (4 resident 128-thread CTAs per SM at 128 registers), then nudge the
+        // split count so the last wave is full: wave quantisation cost 20 % at Pubmed size
+        const int64_t slots = 148 * 4;
+        want = cdiv(slots * 3, c->nb);
+        double best = 1e30;
+        int64_t best_s = want;
+        for (int64_t s = (want + 1) / 2; s <= want * 2 && s <= max_splits; ++s) {
+            const int64_t jc = cdiv(cdiv(n, s), c->JT) * c->JT;
+            const int64_t real = cdiv(n, jc);
+            const double ctas = (double)(c->nb * real);
+            const double waves = (double)cdiv((int64_t)ctas, slots);
+            const double cost = waves * (double)jc;     // time ~ waves x work per CTA
+            if (cost < best - 1e-9) { best = cost; best_s = s; }
+        }
+        want = best_s;
+    }
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;
     c->j_chunk = cdiv(cdiv(n, want), c->JT) * c->JT;
@@ -61,8 +77,12 @@ dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, in
     const int64_t jbeg = (int64_t)blockIdx.y * j_chunk;
     const int64_t jend = min(n, jbeg + j_chunk);
 
-    float zi[R][D];
-    float acc[R][D];
+    // Packed fp32x2 FMAs (Blackwell FFMA2, __ffma2_rn): the dot product keeps an (even, odd)
+    // pair of partial sums, the gradient accumulator is updated two columns per instruction --
+    // half the issue slots of scalar FFMA for the 2d FMAs per pair.
+    constexpr int D2 = D / 2;
+    float2 zi[R][D2];
+    float2 acc[R][D2];
     float lsum[R];
     bool valid[R];
 #pragma unroll
@@ -71,9 +91,10 @@ dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, in
         valid[r] = i < n;
         lsum[r] = 0.f;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            zi[r][k] = (valid[r] && k < d) ? __ldg(Zd + i * ldz + k) : 0.f;
-            acc[r][k] = 0.f;
+        for (int k = 0; k < D2; ++k) {
+            zi[r][k].x = (valid[r] && 2 * k < d) ? __ldg(Zd + i * ldz + 2 * k) : 0.f;
+            zi[r][k].y = (valid[r] && 2 * k + 1 < d) ? __ldg(Zd + i * ldz + 2 * k + 1) : 0.f;
+            acc[r][k] = make_float2(0.f, 0.f);
         }
     }
 
@@ -87,23 +108,26 @@ dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, in
         __syncthreads();
 #pragma unroll 2
         for (int jj = 0; jj < jcount; ++jj) {
-            float zj[D];
+            float2 zj[D2];
 #pragma unroll
             for (int k4 = 0; k4 < D / 4; ++k4) {
                 const float4 q = *reinterpret_cast<const float4 *>(&Zs[jj][k4 * 4]);
-                zj[k4 * 4 + 0] = q.x; zj[k4 * 4 + 1] = q.y; zj[k4 * 4 + 2] = q.z; zj[k4 * 4 + 3] = q.w;
+                zj[k4 * 2 + 0] = make_float2(q.x, q.y);
+                zj[k4 * 2 + 1] = make_float2(q.z, q.w);
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float x = 0.f;
+                float2 x2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < D; ++k) x = fmaf(zi[r][k], zj[k], x);
+                for (int k = 0; k < D2; ++k) x2 = __ffma2_rn(zi[r][k], zj[k], x2);
+                const float x = x2.x + x2.y;
                 float l, sg;
                 softplus_parts(x, l, sg);
                 if (LOSS) lsum[r] += fmaxf(x, 0.f) + l;
                 if (GRAD) {
+                    const float2 sg2 = make_float2(sg, sg);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) acc[r][k] = fmaf(sg, zj[k], acc[r][k]);
+                    for (int k = 0; k < D2; ++k) acc[r][k] = __ffma2_rn(sg2, zj[k], acc[r][k]);
                 }
             }
         }
@@ -117,7 +141,7 @@ dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, in
             float4 *o = reinterpret_cast<float4 *>(dz_part + ((int64_t)blockIdx.y * n + i) * D);
 #pragma unroll
             for (int k4 = 0; k4 < D / 4; ++k4)
-                o[k4] = make_float4(acc[r][k4 * 4], acc[r][k4 * 4 + 1], acc[r][k4 * 4 + 2], acc[r][k4 * 4 + 3]);
+                o[k4] = make_float4(acc[r][k4 * 2].x, acc[r][k4 * 2].y, acc[r][k4 * 2 + 1].x, acc[r][k4 * 2 + 1].y);
         }
     }
     if (LOSS) {

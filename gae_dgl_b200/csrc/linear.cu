@@ -24,11 +24,11 @@ struct GemmArgs {
     int act;
 };
 
-constexpr int BM = 64, BK = 16, GEMM_THREADS = 128;
+constexpr int BK = 16, GEMM_THREADS = 128;
 
-template <int BN, bool A_KC, bool B_KC>
+template <int BM, int BN, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmArgs g) {
-    constexpr int TM = 4, TN = BN / 8;
+    constexpr int TM = BM / 16, TN = BN / 8;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -95,21 +95,29 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmArgs g) {
     }
 }
 
-template <bool A_KC, bool B_KC>
-static cudaError_t launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
-    if (g.M == 0 || g.N == 0) return cudaSuccess;
+template <int BM, bool A_KC, bool B_KC>
+static cudaError_t launch_gemm_bm(const GemmArgs &g, int splits, cudaStream_t st) {
     if (g.N <= 16) {
         dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 16), splits);
-        sgemm_kernel<16, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+        sgemm_kernel<BM, 16, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
     } else if (g.N <= 32) {
         dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 32), splits);
-        sgemm_kernel<32, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+        sgemm_kernel<BM, 32, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
     } else {
         dim3 grid((unsigned)cdiv(g.M, BM), (unsigned)cdiv(g.N, 64), splits);
-        sgemm_kernel<64, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
+        sgemm_kernel<BM, 64, A_KC, B_KC><<<grid, GEMM_THREADS, 0, st>>>(g);
     }
     count_launch();
     return cudaGetLastError();
+}
+
+template <bool A_KC, bool B_KC>
+static cudaError_t launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
+    if (g.M == 0 || g.N == 0) return cudaSuccess;
+    // 32-row tiles when M is small (dW: M = d_out) or when 64-row tiles would not fill the chip
+    const int64_t ctas64 = cdiv(g.M, 64) * cdiv(g.N, g.N <= 16 ? 16 : g.N <= 32 ? 32 : 64) * splits;
+    if (g.M <= 32 || ctas64 < 148 * 4) return launch_gemm_bm<32, A_KC, B_KC>(g, splits, st);
+    return launch_gemm_bm<64, A_KC, B_KC>(g, splits, st);
 }
 
 // out[i] = sum_z part[z*stride + i] in fixed z order (deterministic split-K reduce)
@@ -150,12 +158,14 @@ __global__ void colsum_masked_kernel(const float *__restrict__ dH, int64_t ld_dh
     }
 }
 
+static inline int64_t db_rows_per_block(int64_t n) { return n / 2048 > 256 ? n / 2048 : 256; }
+
 static void bwd_split_config(int64_t n, int32_t d_in, int32_t d_out, int *splits, int64_t *k_chunk) {
     // enough CTAs to fill 148 SMs a few times, chunks a multiple of BK, at most 1024 splits
-    const int64_t tiles = cdiv(d_out, BM) * cdiv(d_in, 64);
-    int64_t want = cdiv(148 * 4, tiles);
+    const int64_t tiles = cdiv(d_out, d_out <= 32 ? 32 : 64) * cdiv(d_in, d_in <= 16 ? 16 : d_in <= 32 ? 32 : 64);
+    int64_t want = cdiv(148 * 6, tiles);
     int64_t chunk = cdiv(cdiv(n, want), BK) * BK;
-    if (chunk < 256) chunk = 256;
+    if (chunk < 64) chunk = 64;
     int64_t s = cdiv(n, chunk);
     if (s > 1024) { chunk = cdiv(cdiv(n, 1024), BK) * BK; s = cdiv(n, chunk); }
     if (s < 1) s = 1;
@@ -188,7 +198,7 @@ extern "C" int64_t gae_linear_bwd_ws_bytes(int64_t n, int32_t d_in, int32_t d_ou
     if (n <= 0 || d_in <= 0 || d_out <= 0) return 0;
     int splits; int64_t chunk;
     bwd_split_config(n, d_in, d_out, &splits, &chunk);
-    const int64_t db_blocks = cdiv(n, 2048);
+    const int64_t db_blocks = cdiv(n, db_rows_per_block(n));
     return (int64_t)sizeof(float) * ((int64_t)splits * d_out * d_in + db_blocks * d_out);
 }
 
@@ -231,7 +241,7 @@ extern "C" int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *
     }
     // db[j] = sum_n dPre[n,j]
     {
-        const int64_t rows_per_block = 2048;
+        const int64_t rows_per_block = db_rows_per_block(n);
         const int64_t blocks = cdiv(n, rows_per_block);
         colsum_masked_kernel<<<(unsigned)blocks, dim3(32, 8), 0, st>>>(dH, ld_dh, mask, ld_out, mask != nullptr, n,
                                                                        d_out, rows_per_block, part_b);

@@ -21,7 +21,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // Reference gae.py:70: F.dropout(z, p) with training=True always.  Zd = Z * keep / (1-p).
 __global__ void dropout_fwd_kernel(const float *__restrict__ Z, int64_t ldz, float *__restrict__ Zd,
                                    int64_t ldzd, uint8_t *__restrict__ mask, int64_t n, int d, float p,
-                                   float scale, uint64_t seed, uint64_t offset, int mask_mode) {
+                                   float scale, uint64_t seed, uint64_t offset, int mask_mode,
+                                   const uint64_t *__restrict__ rng_state) {
+    if (rng_state) {  // device-resident Philox state: CUDA-graph replays draw fresh masks
+        seed = rng_state[0];
+        offset = rng_state[1];
+    }
     const int64_t total = n * d;
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
     if (q * 4 >= total) return;
@@ -48,6 +53,8 @@ __global__ void dropout_fwd_kernel(const float *__restrict__ Z, int64_t ldz, flo
         Zd[row * ldzd + c] = keep ? Z[row * ldz + c] * scale : 0.f;
     }
 }
+
+__global__ void rng_advance_kernel(uint64_t *state, uint64_t inc) { state[1] += inc; }
 
 __global__ void dropout_bwd_kernel(const float *__restrict__ dZd, int64_t ld_dzd,
                                    const uint8_t *__restrict__ mask, float *__restrict__ dZ, int64_t ld_dz,
@@ -117,6 +124,22 @@ __global__ void pull_rows_p2p_kernel(const float *const *__restrict__ peers, con
     reinterpret_cast<float4 *>(out + r * ldo)[c] = v;
 }
 
+// one-sided halo PUSH: the owner reads its own rows (local HBM / L2) and stores them straight
+// into each peer's halo region over NVLink.  Stores are posted (no round trip), so this sustains
+// far more NVLink bandwidth than remote loads; it also fuses the "pack" step of an all-to-all
+// into the transfer -- no staging buffer on either side.
+__global__ void push_rows_p2p_kernel(const float *__restrict__ X, int64_t ldx, const int64_t *__restrict__ send_idx,
+                                     const int32_t *__restrict__ dst_peer, const int64_t *__restrict__ dst_row,
+                                     float *const *__restrict__ peers, int64_t m, int64_t ld_peer, int d4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = t / d4;
+    const int c = (int)(t % d4);
+    if (r >= m) return;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(X + send_idx[r] * ldx) + c);
+    float4 *dst = reinterpret_cast<float4 *>(peers[dst_peer[r]] + dst_row[r] * ld_peer) + c;
+    *dst = v;
+}
+
 }  // namespace gae
 
 using namespace gae;
@@ -131,7 +154,24 @@ extern "C" int gae_dropout_fwd_f32(const float *Z, int64_t ldz, float *Zd, int64
     GAE_CHECK_ARG(ldz >= d && ldzd >= d, "leading dimension too small");
     const int64_t groups = cdiv(n * d, 4);
     dropout_fwd_kernel<<<(unsigned)cdiv(groups, 256), 256, 0, (cudaStream_t)stream>>>(
-        Z, ldz, Zd, ldzd, mask, n, d, p, 1.0f / (1.0f - p), seed, offset, mask_mode);
+        Z, ldz, Zd, ldzd, mask, n, d, p, 1.0f / (1.0f - p), seed, offset, mask_mode, nullptr);
+    GAE_LAUNCH_CHECK();
+    return GAE_OK;
+}
+
+extern "C" int gae_dropout_fwd_devrng_f32(const float *Z, int64_t ldz, float *Zd, int64_t ldzd, uint8_t *mask,
+                                          int64_t n, int32_t d, float p, uint64_t *rng_state, void *stream) {
+    GAE_CHECK_ARG(n >= 0 && d > 0, "bad sizes");
+    GAE_CHECK_ARG(p >= 0.f && p < 1.f, "p must be in [0,1)");
+    if (n == 0) return GAE_OK;
+    GAE_CHECK_ARG(Z && Zd && mask && rng_state, "null pointer");
+    GAE_CHECK_ARG(ldz >= d && ldzd >= d, "leading dimension too small");
+    const int64_t groups = cdiv(n * d, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    dropout_fwd_kernel<<<(unsigned)cdiv(groups, 256), 256, 0, st>>>(Z, ldz, Zd, ldzd, mask, n, d, p, 1.0f / (1.0f - p),
+                                                                    0, 0, 0, rng_state);
+    GAE_LAUNCH_CHECK();
+    rng_advance_kernel<<<1, 1, 0, st>>>(rng_state, (uint64_t)groups);
     GAE_LAUNCH_CHECK();
     return GAE_OK;
 }
@@ -192,6 +232,19 @@ extern "C" int gae_pull_rows_p2p_f32(const float *const *peer_ptrs, const int32_
     GAE_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && ld_out % 4 == 0 && aligned16(out), "p2p pull needs 16-byte aligned rows");
     pull_rows_p2p_kernel<<<(unsigned)cdiv(m * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(
         peer_ptrs, owner, idx, m, ldx, d / 4, out, ld_out);
+    GAE_LAUNCH_CHECK();
+    return GAE_OK;
+}
+
+extern "C" int gae_push_rows_p2p_f32(const float *X, int64_t ldx, const int64_t *send_idx, const int32_t *dst_peer,
+                                     const int64_t *dst_row, float *const *peer_ptrs, int64_t m, int64_t ld_peer,
+                                     int32_t d, void *stream) {
+    GAE_CHECK_ARG(m >= 0 && d > 0, "bad sizes");
+    if (m == 0) return GAE_OK;
+    GAE_CHECK_ARG(X && send_idx && dst_peer && dst_row && peer_ptrs, "null pointer");
+    GAE_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && ld_peer % 4 == 0 && aligned16(X), "p2p push needs 16-byte aligned rows");
+    push_rows_p2p_kernel<<<(unsigned)cdiv(m * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        X, ldx, send_idx, dst_peer, dst_row, peer_ptrs, m, ld_peer, d / 4);
     GAE_LAUNCH_CHECK();
     return GAE_OK;
 }

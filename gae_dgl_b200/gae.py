@@ -89,23 +89,27 @@ class InnerProductDecoder(nn.Module):
         self.dropout = dropout
         self.activation = activation
 
-    @staticmethod
-    def _rng():
-        # seed/offset for the Philox mask come from torch's generator so torch.manual_seed
-        # controls them; two int64 draws on the host, no device sync
-        s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
-        return int(s[0]), int(s[1])
+    def _rng_state(self, device) -> torch.Tensor:
+        """Device-resident Philox state {seed, offset}, created on first use from torch's host
+        generator (so torch.manual_seed controls it) and advanced on-stream by every draw: no
+        per-step host RNG call, and captured CUDA graphs draw a fresh mask on each replay."""
+        st = getattr(self, "_philox", None)
+        if st is None or st.device != device:
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+            st = torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
+            self._philox = st
+        return st
 
     def forward(self, z, mask: Optional[torch.Tensor] = None):
-        seed, offset = (0, 0) if mask is not None else self._rng()
-        x = ops.DecoderLogitsFunction.apply(z, float(self.dropout), mask, seed, offset)
+        st = None if mask is not None else self._rng_state(z.device)
+        x = ops.DecoderLogitsFunction.apply(z, float(self.dropout), mask, st)
         return self.activation(x)
 
     def loss(self, z, g: DGLGraph, pos_weight: float, mask: Optional[torch.Tensor] = None):
         """Fused path: mean BCE-with-logits(z_d z_d^T, A, pos_weight) without the N x N arrays
         (replaces gae.py:71 + train_inductive.py:44,48)."""
-        seed, offset = (0, 0) if mask is not None else self._rng()
-        return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, seed, offset)
+        st = None if mask is not None else self._rng_state(z.device)
+        return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, st)
 
 
 def pos_weight_of(g: DGLGraph, transductive: bool = False) -> float:

@@ -195,22 +195,31 @@ def linear_bwd(Y: torch.Tensor, W: torch.Tensor, H: torch.Tensor, dH: torch.Tens
 
 
 def dropout_fwd(Z: torch.Tensor, p: float, mask: Optional[torch.Tensor] = None,
-                seed: int = 0, offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Zd = Z * keep / (1-p).  `mask` (uint8/bool keep-mask [n,d]) is READ when given,
-    otherwise drawn from Philox(seed, offset) and returned."""
+                seed: int = 0, offset: int = 0, rng_state: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Zd = Z * keep / (1-p).  `mask` (uint8/bool keep-mask [n,d]) is READ when given; otherwise
+    the mask is drawn from Philox -- from the device-resident state `rng_state` (int64[2], advanced
+    on the stream: CUDA-graph safe) when given, else from the host-side (seed, offset)."""
     Z = as_rows(Z, "Z")
     n, d = Z.shape
     Zd = alloc_rows(n, d, Z.device)
+    lib = _lib.load()
     if mask is None:
         m = torch.empty((n, d), dtype=torch.uint8, device=Z.device)
+        if rng_state is not None:
+            _require_cuda(rng_state, "rng_state", torch.int64)
+            rc = lib.gae_dropout_fwd_devrng_f32(_ptr(Z), _ld(Z), _ptr(Zd), _ld(Zd), _ptr(m), n, d, float(p),
+                                                _ptr(rng_state), _stream())
+            _lib.check(rc, "gae_dropout_fwd_devrng_f32")
+            return Zd, m
         mode = 0
     else:
         m = mask.to(device=Z.device, dtype=torch.uint8).contiguous()
         if m.shape != (n, d):
             raise GaeError("dropout mask shape mismatch")
         mode = 1
-    rc = _lib.load().gae_dropout_fwd_f32(_ptr(Z), _ld(Z), _ptr(Zd), _ld(Zd), _ptr(m), n, d, float(p),
-                                         int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), mode, _stream())
+    rc = lib.gae_dropout_fwd_f32(_ptr(Z), _ld(Z), _ptr(Zd), _ld(Zd), _ptr(m), n, d, float(p),
+                                 int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), mode, _stream())
     _lib.check(rc, "gae_dropout_fwd_f32")
     return Zd, m
 
@@ -320,10 +329,10 @@ class DecoderLossFunction(torch.autograd.Function):
     produced in the same pass as the loss and scaled by grad_output in backward."""
 
     @staticmethod
-    def forward(ctx, Z, graph, pos_weight, p, mask, seed, offset):
+    def forward(ctx, Z, graph, pos_weight, p, mask, rng_state):
         csr, csr_t = graph.csr(), graph.csr_t()
         need_grad = Z.requires_grad
-        Zd, m = dropout_fwd(Z, p, mask, seed, offset)
+        Zd, m = dropout_fwd(Z, p, mask, rng_state=rng_state)
         loss, dZd_unit = decoder_bce(Zd, csr.rowptr, csr.col, csr_t.rowptr, csr_t.col, pos_weight,
                                      want_loss=True, want_grad=need_grad)
         ctx.p = p
@@ -334,9 +343,9 @@ class DecoderLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         if ctx.dZd_unit is None:
-            return (None,) * 7
+            return (None,) * 6
         dZ = dropout_bwd(ctx.dZd_unit, ctx.mask, ctx.p, grad_scale=g)
-        return dZ, None, None, None, None, None, None
+        return dZ, None, None, None, None, None
 
 
 class DecoderLogitsFunction(torch.autograd.Function):
@@ -344,8 +353,8 @@ class DecoderLogitsFunction(torch.autograd.Function):
     its backward uses torch.matmul on the N x N gradient the caller's dense loss produced."""
 
     @staticmethod
-    def forward(ctx, Z, p, mask, seed, offset):
-        Zd, m = dropout_fwd(Z, p, mask, seed, offset)
+    def forward(ctx, Z, p, mask, rng_state):
+        Zd, m = dropout_fwd(Z, p, mask, rng_state=rng_state)
         ctx.p = p
         ctx.save_for_backward(Zd, m)
         return decoder_logits(Zd)
@@ -354,4 +363,4 @@ class DecoderLogitsFunction(torch.autograd.Function):
     def backward(ctx, G):
         Zd, m = ctx.saved_tensors
         dZd = (G + G.t()) @ Zd
-        return dropout_bwd(dZd, m, ctx.p), None, None, None, None
+        return dropout_bwd(dZd, m, ctx.p), None, None, None

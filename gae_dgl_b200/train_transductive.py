@@ -39,6 +39,7 @@ def build_parser():
     parser.add_argument('--variational', action='store_true')
     parser.add_argument('--dense_decoder', action='store_true', help="reference's materialised N x N loss")
     parser.add_argument('--log_every', type=int, default=50)
+    parser.add_argument('--no_cuda_graph', action='store_true', help='run every epoch eagerly')
     return parser
 
 
@@ -59,7 +60,7 @@ def train(args, features, g, device, verbose=True):
     model = (VGAE if args.variational else GAE)(in_feats, args.hidden_dims)   # :41
     model.to(device)
     model.train()
-    optim = torch.optim.Adam(model.parameters(), lr=args.lr)                    # :43
+    optim = torch.optim.Adam(model.parameters(), lr=args.lr, capturable=True)   # :43 (capturable: CUDA-graph replay)
     g.to(device)
     features = features.to(device)
 
@@ -74,20 +75,41 @@ def train(args, features, g, device, verbose=True):
         adj = g.adjacency_matrix().to_dense()
         pw_t = torch.tensor([pos_weight], device=device)
 
-    losses = []
-    for epoch in range(args.n_epochs):
+    def loss_fn():
         g.ndata['h'] = features                     # repaired :46 / gae.py:53 overwrite
         if args.dense_decoder:
-            adj_logits = model.forward(g)
-            loss = BCELoss(adj_logits, adj, pos_weight=pw_t)
-        else:
-            loss = model.loss(g, pos_weight=pos_weight)
-        optim.zero_grad()
-        loss.backward()
-        optim.step()
-        losses.append(loss.item())
+            return BCELoss(model.forward(g), adj, pos_weight=pw_t)
+        return model.loss(g, pos_weight=pos_weight)
+
+    losses = []
+
+    def log(epoch, value):
+        losses.append(value)
         if verbose and (epoch % args.log_every == 0 or epoch == args.n_epochs - 1):
-            print('Epoch: {:02d} | Loss: {:.5f}'.format(epoch, losses[-1]))
+            print('Epoch: {:02d} | Loss: {:.5f}'.format(epoch, value))
+
+    use_graph = not getattr(args, 'no_cuda_graph', False) and not args.dense_decoder and args.n_epochs > 8
+    if use_graph:
+        # the graph is static: capture one step (3 eager warm-up epochs, then replay)
+        from .graphed import GraphedTrainStep
+        step = GraphedTrainStep(model, optim, loss_fn, warmup=3)
+        for epoch, l in enumerate(step.warmup_losses):
+            log(epoch, float(l))
+        pending = []
+        for epoch in range(len(step.warmup_losses), args.n_epochs):
+            pending.append(step().clone())          # no host sync inside the loop
+            if len(pending) >= args.log_every or epoch == args.n_epochs - 1:
+                vals = torch.stack(pending).tolist()
+                for k, v in enumerate(vals):
+                    log(epoch - len(vals) + 1 + k, v)
+                pending = []
+    else:
+        for epoch in range(args.n_epochs):
+            loss = loss_fn()
+            optim.zero_grad()
+            loss.backward()
+            optim.step()
+            log(epoch, loss.item())
     return model, losses
 
 

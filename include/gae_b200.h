@@ -117,6 +117,11 @@ int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *W, const fl
 int gae_dropout_fwd_f32(const float *Z, int64_t ldz, float *Zd, int64_t ldzd, uint8_t *mask,
                         int64_t n, int32_t d, float p, uint64_t seed, uint64_t offset,
                         int32_t mask_mode, void *stream);
+/* Same with the Philox state {seed, offset} in DEVICE memory (uint64[2]); the offset is advanced
+ * on the stream after the draw, so a captured CUDA graph draws a fresh mask on every replay. */
+int gae_dropout_fwd_devrng_f32(const float *Z, int64_t ldz, float *Zd, int64_t ldzd,
+                               uint8_t *mask, int64_t n, int32_t d, float p,
+                               uint64_t *rng_state, void *stream);
 /* dZ = dZd * mask / (1-p) * (*grad_scale or 1 if NULL)  */
 int gae_dropout_bwd_f32(const float *dZd, int64_t ld_dzd, const uint8_t *mask, float *dZ,
                         int64_t ld_dz, int64_t n, int32_t d, float p, const float *grad_scale,
@@ -165,7 +170,14 @@ int gae_gather_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t
 int gae_pull_rows_p2p_f32(const float *const *peer_ptrs, const int32_t *owner,
                           const int64_t *idx, int64_t m, int64_t ldx, int32_t d, float *out,
                           int64_t ld_out, void *stream);
-/* CUDA IPC plumbing for the pull path: 64-byte handles. */
+/* One-sided halo PUSH (the default exchange): for i in [0,m): peer_ptrs[dst_peer[i]][dst_row[i],:]
+ * = X[send_idx[i],:].  The owner reads its own rows and stores them into the peers' halo regions
+ * over NVLink (posted writes); fuses the pack step of an all-to-all into the transfer. */
+int gae_push_rows_p2p_f32(const float *X, int64_t ldx, const int64_t *send_idx,
+                          const int32_t *dst_peer, const int64_t *dst_row,
+                          float *const *peer_ptrs, int64_t m, int64_t ld_peer, int32_t d,
+                          void *stream);
+/* CUDA IPC plumbing for the pull / push paths: 64-byte handles. */
 int gae_ipc_get_handle(const void *dev_ptr, uint8_t handle_out[64], int64_t *offset_out);
 int gae_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out);
 int gae_ipc_close_handle(void *dev_ptr);

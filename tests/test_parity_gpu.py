@@ -391,3 +391,40 @@ def test_trainers_run_and_learn(cuda, tmp_path):
     assert len(tl2) == 1
     losses = train_transductive.main(["--dataset", "cora", "--n_epochs", "30", "--save_dir", str(tmp_path), "--seed", "0"])
     assert losses[-1] < losses[0]
+
+
+def test_cuda_graph_step_matches_eager(cuda):
+    """The captured train step replays the same arithmetic as the eager step (same Philox stream:
+    both start from the same device RNG state) and draws a fresh dropout mask on every replay."""
+    from gae_dgl_b200.graphed import GraphedTrainStep
+    g, X = synthetic.planetoid_like("cora", seed=2)
+    g.to(cuda)
+    Xd = X.to(cuda)
+    pw = G.pos_weight_of(g, transductive=True)
+
+    def make():
+        torch.manual_seed(11)
+        m = G.GAE(1433, [32, 16]).to(cuda)
+        o = torch.optim.Adam(m.parameters(), lr=1e-2, capturable=True)
+
+        def loss_fn():
+            g.ndata["h"] = Xd
+            return m.loss(g, pos_weight=pw)
+        return m, o, loss_fn
+
+    m1, o1, f1 = make()
+    eager = []
+    for _ in range(8):
+        o1.zero_grad(set_to_none=True)
+        l = f1()
+        l.backward()
+        o1.step()
+        eager.append(float(l))
+    m2, o2, f2 = make()
+    step = GraphedTrainStep(m2, o2, f2, warmup=3)
+    graphed = [float(x) for x in step.warmup_losses] + [float(step().clone()) for _ in range(5)]
+    assert len(set(graphed)) == len(graphed)                      # masks differ per replay
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 1e-5 * abs(a), (eager, graphed)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6)

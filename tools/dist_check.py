@@ -21,7 +21,7 @@ def main():
     scale, n_edges, d = 16, 2_000_000, 64
     n = 1 << scale
     ok = True
-    for exchange in ("nccl", "p2p"):
+    for exchange in ("nccl", "p2p", "push"):
         part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange)
         Yf = part.fwd().clone()
         Yb = part.bwd().clone()
