@@ -20,12 +20,18 @@ class HubPlanStruct(Structure):
     """Mirror of gae_hub_plan_t."""
     _fields_ = [
         ("seg_len", c_int32),
-        ("_pad", c_int32),
+        ("short_max", c_int32),
         ("n_long", c_int64),
         ("n_seg", c_int64),
         ("long_row", c_void_p),
         ("long_seg_ptr", c_void_p),
         ("seg_row", c_void_p),
+        ("n_empty", c_int64),
+        ("n_short", c_int64),
+        ("n_mid", c_int64),
+        ("empty_rows", c_void_p),
+        ("short_rows", c_void_p),
+        ("mid_rows", c_void_p),
     ]
 
 
@@ -38,6 +44,8 @@ SIGNATURES = {
     "gae_launch_count": (c_int64, []),
     "gae_hub_plan_count_host": (c_int, [c_void_p, c_int64, c_int32, POINTER(c_int64), POINTER(c_int64)]),
     "gae_hub_plan_fill_host": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gae_row_bins_host": (c_int, [c_void_p, c_int64, c_int32, c_int32, POINTER(c_int64 * 3), c_void_p, c_void_p,
+                                  c_void_p]),
     "gae_spmm_csr_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                  c_int32, POINTER(HubPlanStruct), c_void_p, c_int32, c_void_p]),
     "gae_spmm_csr_f32_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,

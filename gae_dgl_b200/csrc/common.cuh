@@ -20,6 +20,7 @@ enum TuningIdx {
     T_SPMM_ROWS_PER_WARP,// 1 = warp per row, 2 = half-warp per row (d <= 64)
     T_DEC_SPLITS,        // 0 = auto
     T_SPMM_STAGES,       // streaming variant: batches of 32 rows in flight per warp (2/3/4)
+    T_SPMM_BINS,         // 1 = use the plan's degree bins when present, 0 = single row pass
     T_COUNT
 };
 

@@ -37,6 +37,8 @@ struct SpmmArgs {
     const int32_t *long_row;
     const int64_t *long_seg_ptr;
     const int32_t *seg_row;
+    // optional indirection: item -> row (degree-binned launches)
+    const int32_t *row_list;
 };
 
 // All gathers are `asm volatile` so that their program order (U index loads, then U row
@@ -86,13 +88,14 @@ __global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
     float *out = nullptr;
     if (active) {
         if (!SEG) {
-            start = __ldg(a.rowptr + item);
-            end = __ldg(a.rowptr + item + 1);
+            const int64_t row = a.row_list ? (int64_t)__ldg(a.row_list + item) : item;
+            start = __ldg(a.rowptr + row);
+            end = __ldg(a.rowptr + row + 1);
             if (a.seg_len > 0 && end - start > (int64_t)a.seg_len) {  // hub row: segment pass
                 active = false;
                 start = end = 0;
             }
-            out = a.Y + item * a.ldy;
+            out = a.Y + row * a.ldy;
         } else {
             const int32_t k = __ldg(a.seg_row + item);
             const int64_t row = __ldg(a.long_row + k);
@@ -161,6 +164,62 @@ __global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
             }
         }
     }
+}
+
+// Short rows (1..U in-edges): LPR lanes x CPL float4 cover a row, 32/LPR rows per warp, every
+// gather of the row in flight at once (U x CPL 128-bit loads per lane) -- one latency per row
+// instead of a warp and a dependent chain per row.
+template <int LPR, int CPL, int U>
+__global__ void __launch_bounds__(128, 8) spmm_short_rows_kernel(const SpmmArgs a) {
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const int64_t item = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + grp;
+    if (item >= a.n_items) return;
+    const int64_t row = __ldg(a.row_list + item);
+    const int64_t start = __ldg(a.rowptr + row);
+    const int len = (int)(__ldg(a.rowptr + row + 1) - start);
+    const int32_t *cp = a.col + start;
+    const int ldx = (int)a.ldx;
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ld_idx(cp + min(u, len - 1));
+    float4 v[U][CPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int c4 = q * LPR + sub;
+            v[u][q] = gather_f4<0>(a.X + (int64_t)c[u] * ldx + (c4 * 4 < a.d ? c4 : 0) * 4, 0);
+        }
+    float4 acc[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) acc[q] = v[0][q];
+#pragma unroll
+    for (int u = 1; u < U; ++u)
+        if (u < len) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) f4_add(acc[q], v[u][q]);
+        }
+    float *out = a.Y + row * a.ldy;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int c4 = q * LPR + sub;
+        if (c4 * 4 + 4 <= a.d) {
+            float *o = out + c4 * 4;
+            if (a.accumulate) f4_add(acc[q], *reinterpret_cast<const float4 *>(o));
+            *reinterpret_cast<float4 *>(o) = acc[q];
+        }
+    }
+}
+
+// Empty rows: streaming zero fill (Y = A X must still define them).
+__global__ void spmm_zero_rows_kernel(const int32_t *__restrict__ rows, int64_t n, float *__restrict__ Y,
+                                      int64_t ldy, int d4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = t / d4;
+    if (r >= n) return;
+    st_stream_f4(Y + (int64_t)__ldg(rows + r) * ldy + (t % d4) * 4, f4_zero());
 }
 
 // Ordered reduce of the segment partials of each long row: Y[row] (+)= sum_s P[seg_s].
@@ -302,7 +361,30 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
         }
         return GAE_OK;
     }
-    GAE_CUDA(launch_vec<false>(a, rpw, unroll, cache, block, st));
+    const bool binned = plan && plan->mid_rows && plan->short_rows && plan->empty_rows && d % 4 == 0 && d <= 64 &&
+                        plan->short_max == 4 && !vals && tuning(T_SPMM_BINS) != 0;
+    if (binned) {
+        // degree-binned row pass: zero fill | short rows 4 per warp | a warp per remaining row
+        if (plan->n_empty > 0 && !accumulate) {
+            const int64_t threads = plan->n_empty * (d / 4);
+            spmm_zero_rows_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(plan->empty_rows, plan->n_empty, Y, ldy, d / 4);
+            GAE_LAUNCH_CHECK();
+        }
+        if (plan->n_short > 0) {
+            SpmmArgs sh = a;
+            sh.row_list = plan->short_rows; sh.n_items = plan->n_short;
+            const int64_t warps = cdiv(plan->n_short, 4);
+            spmm_short_rows_kernel<8, 2, 4><<<(unsigned)cdiv(warps, 4), 128, 0, st>>>(sh);
+            GAE_LAUNCH_CHECK();
+        }
+        if (plan->n_mid > 0) {
+            SpmmArgs md = a;
+            md.row_list = plan->mid_rows; md.n_items = plan->n_mid;
+            GAE_CUDA(launch_vec<false>(md, rpw, unroll, cache, block, st));
+        }
+    } else {
+        GAE_CUDA(launch_vec<false>(a, rpw, unroll, cache, block, st));
+    }
     if (use_plan) {
         const int64_t ldp = (int64_t)((d + 3) / 4) * 4;
         SpmmArgs s = a;
@@ -341,6 +423,21 @@ extern "C" int gae_hub_plan_count_host(const int64_t *rowptr, int64_t n_rows, in
         if (deg > seg_len) { ++nl; ns += (deg + seg_len - 1) / seg_len; }
     }
     *n_long = nl; *n_seg = ns;
+    return GAE_OK;
+}
+
+extern "C" int gae_row_bins_host(const int64_t *rowptr, int64_t n_rows, int32_t seg_len, int32_t short_max,
+                                 int64_t counts[3], int32_t *empty_rows, int32_t *short_rows, int32_t *mid_rows) {
+    GAE_CHECK_ARG(rowptr && counts, "null pointer");
+    GAE_CHECK_ARG(seg_len > 0 && short_max > 0 && n_rows >= 0 && n_rows < ((int64_t)1 << 31), "bad sizes");
+    int64_t ne = 0, ns = 0, nm = 0;
+    for (int64_t v = 0; v < n_rows; ++v) {
+        const int64_t deg = rowptr[v + 1] - rowptr[v];
+        if (deg == 0) { if (empty_rows) empty_rows[ne] = (int32_t)v; ++ne; }
+        else if (deg <= short_max) { if (short_rows) short_rows[ns] = (int32_t)v; ++ns; }
+        else if (deg <= seg_len) { if (mid_rows) mid_rows[nm] = (int32_t)v; ++nm; }
+    }
+    counts[0] = ne; counts[1] = ns; counts[2] = nm;
     return GAE_OK;
 }
 

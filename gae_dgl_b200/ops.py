@@ -20,7 +20,7 @@ ACT_IDENTITY = 0
 ACT_RELU = 1
 DEC_LOSS = 1
 DEC_GRAD = 2
-DEFAULT_SEG_LEN = 256
+DEFAULT_SEG_LEN = 512
 
 
 # ------------------------------------------------------------------------------------------
@@ -85,6 +85,10 @@ def _ld(t: torch.Tensor) -> int:
 # hub plan
 # ------------------------------------------------------------------------------------------
 
+SHORT_MAX = 4
+BIN_MIN_ROWS = 1 << 16     # below this a single row pass wins (fewer launches)
+
+
 @dataclass
 class HubPlan:
     seg_len: int
@@ -94,6 +98,7 @@ class HubPlan:
     long_seg_ptr: torch.Tensor
     seg_row: torch.Tensor
     struct: HubPlanStruct
+    bins: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None   # (empty, short, mid) row lists
 
     def workspace(self, d: int, device) -> Optional[torch.Tensor]:
         if self.n_seg == 0:
@@ -101,9 +106,10 @@ class HubPlan:
         return torch.empty((self.n_seg, round_up4(d)), dtype=torch.float32, device=device)
 
 
-def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN) -> HubPlan:
-    """Split rows with in-degree > seg_len into fixed-length segments (gae_hub_plan_*_host).
-    Runs once per graph on the host copy of rowptr."""
+def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN, bins: Optional[bool] = None) -> HubPlan:
+    """Split rows with in-degree > seg_len into fixed-length segments (gae_hub_plan_*_host) and,
+    for large graphs, bin the remaining rows by degree (gae_row_bins_host).  Runs once per graph
+    on the host copy of rowptr."""
     lib = _lib.load()
     rp = rowptr.detach().to("cpu", torch.int64).contiguous().numpy()
     n_rows = rp.shape[0] - 1
@@ -120,9 +126,24 @@ def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN) -> HubP
     t_long = torch.from_numpy(long_row).to(dev)
     t_ptr = torch.from_numpy(long_seg_ptr).to(dev)
     t_seg = torch.from_numpy(seg_row).to(dev)
-    st = HubPlanStruct(seg_len=seg_len, _pad=0, n_long=nl, n_seg=ns, long_row=t_long.data_ptr(),
+    st = HubPlanStruct(seg_len=seg_len, short_max=SHORT_MAX, n_long=nl, n_seg=ns, long_row=t_long.data_ptr(),
                        long_seg_ptr=t_ptr.data_ptr(), seg_row=t_seg.data_ptr())
-    return HubPlan(seg_len, nl, ns, t_long, t_ptr, t_seg, st)
+    plan = HubPlan(seg_len, nl, ns, t_long, t_ptr, t_seg, st)
+    if bins is None:
+        bins = n_rows >= BIN_MIN_ROWS
+    if bins:
+        counts = (ctypes.c_int64 * 3)()
+        _lib.check(lib.gae_row_bins_host(rp.ctypes.data, n_rows, seg_len, SHORT_MAX, ctypes.byref(counts), None, None,
+                                         None), "gae_row_bins_host")
+        arrs = [np.zeros(max(int(c), 1), dtype=np.int32) for c in counts]
+        _lib.check(lib.gae_row_bins_host(rp.ctypes.data, n_rows, seg_len, SHORT_MAX, ctypes.byref(counts),
+                                         arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data),
+                   "gae_row_bins_host")
+        ts = tuple(torch.from_numpy(a).to(dev) for a in arrs)
+        plan.bins = ts
+        st.n_empty, st.n_short, st.n_mid = int(counts[0]), int(counts[1]), int(counts[2])
+        st.empty_rows, st.short_rows, st.mid_rows = (t.data_ptr() for t in ts)
+    return plan
 
 
 # ------------------------------------------------------------------------------------------
@@ -147,7 +168,7 @@ def spmm(rowptr: torch.Tensor, col: torch.Tensor, X: torch.Tensor, plan: Optiona
         if out.shape != (n_rows, d) or (out.stride(1) != 1 and d > 1):
             raise GaeError("out has the wrong shape / layout")
     plan_ref = None
-    if plan is not None and plan.n_seg > 0:
+    if plan is not None and (plan.n_seg > 0 or plan.bins is not None):
         plan_ref = ctypes.byref(plan.struct)
         if partial_ws is None:
             partial_ws = plan.workspace(d, X.device)

@@ -62,14 +62,28 @@ int gae_hub_plan_count_host(const int64_t *rowptr_host, int64_t n_rows, int32_t 
 int gae_hub_plan_fill_host(const int64_t *rowptr_host, int64_t n_rows, int32_t seg_len,
                            int32_t *long_row, int64_t *long_seg_ptr, int32_t *seg_row);
 
+/* Degree bins, same two-call protocol: pass NULL arrays to get counts[3] = {n_empty, n_short,
+ * n_mid}, then arrays of those sizes (row ids ascending within each bin). */
+int gae_row_bins_host(const int64_t *rowptr_host, int64_t n_rows, int32_t seg_len,
+                      int32_t short_max, int64_t counts[3], int32_t *empty_rows,
+                      int32_t *short_rows, int32_t *mid_rows);
+
 typedef struct gae_hub_plan_t {
     int32_t seg_len;             /* edges per segment (> 0)                       */
-    int32_t _pad;
+    int32_t short_max;           /* degree bins: rows with 1..short_max in-edges are "short" */
     int64_t n_long;              /* rows with deg > seg_len                       */
     int64_t n_seg;               /* total segments over those rows                */
     const int32_t *long_row;     /* [n_long]   row id of k-th long row (ascending) */
     const int64_t *long_seg_ptr; /* [n_long+1] prefix sum of segments per long row */
     const int32_t *seg_row;      /* [n_seg]    index k of the long row a segment belongs to */
+    /* Optional degree bins (all NULL / 0 = the row kernel walks every row).  On skewed graphs
+     * most rows are empty or tiny (R-MAT C4: 71 % of the rows hold 2.4 % of the edges) and a
+     * warp per row wastes the machine on them: empty rows get a streaming zero fill, short rows
+     * run four to a warp with all their gathers in flight at once, the rest keep a warp each. */
+    int64_t n_empty, n_short, n_mid;
+    const int32_t *empty_rows;   /* [n_empty] rows with in-degree 0                         */
+    const int32_t *short_rows;   /* [n_short] rows with in-degree in [1, short_max]          */
+    const int32_t *mid_rows;     /* [n_mid]   rows with in-degree in (short_max, seg_len]    */
 } gae_hub_plan_t;
 
 /* ---- K1 / K2: CSR SpMM, Y = A X (sum aggregation) -------------------------------------- */

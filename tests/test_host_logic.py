@@ -78,6 +78,21 @@ def test_hub_plan_host_matches_numpy(lib_built):
     assert plan.n_seg == int(np.sum((deg[long] + 15) // 16))
 
 
+def test_row_bins_host_matches_numpy(lib_built):
+    rng = np.random.default_rng(3)
+    deg = rng.integers(0, 12, size=2000)
+    deg[[5, 900]] = [300, 257]
+    rowptr = np.zeros(2001, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    plan = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256, bins=True)
+    empty, short, mid = (t.numpy() for t in plan.bins)
+    assert empty[:plan.struct.n_empty].tolist() == np.flatnonzero(deg == 0).tolist()
+    assert short[:plan.struct.n_short].tolist() == np.flatnonzero((deg >= 1) & (deg <= 4)).tolist()
+    assert mid[:plan.struct.n_mid].tolist() == np.flatnonzero((deg > 4) & (deg <= 256)).tolist()
+    assert plan.long_row[:plan.n_long].tolist() == [5, 900]
+    assert ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256).bins is None     # small graph: single pass
+
+
 def test_graph_container_matches_oracle_indexing():
     rng = np.random.default_rng(1)
     n, e = 50, 300

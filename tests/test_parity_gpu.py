@@ -51,14 +51,18 @@ def test_spmm_parity(cuda, d, rows_per_warp):
     rp, cl = to_dev(rowptr, col, cuda)
     _lib.set_tuning("spmm_rows_per_warp", rows_per_warp)
     try:
-        for seg_len in (None, 512, 64):
-            plan = ops.build_hub_plan(rp, seg_len) if seg_len else None
+        for seg_len, bins in ((None, False), (512, False), (64, False), (512, True), (64, True)):
+            plan = ops.build_hub_plan(rp, seg_len, bins=bins) if seg_len else None
             if seg_len:
                 assert plan.n_long >= 1
-            for unroll in (4, 8):
+            if bins:   # degree-binned row pass: every row lands in exactly one bin
+                ne, ns, nm = (int(plan.struct.n_empty), int(plan.struct.n_short), int(plan.struct.n_mid))
+                assert ne + ns + nm + plan.n_long == n and ne >= 5
+            for unroll in (2, 4, 8):
                 _lib.set_tuning("spmm_unroll", unroll)
-                Y = ops.spmm(rp, cl, X.to(cuda), plan)
-                assert rel_err(Y, ref) < TOL, (d, seg_len, unroll)
+                Y = torch.full((n, d), float("nan"), device=cuda) if d % 4 == 0 else None
+                Y = ops.spmm(rp, cl, X.to(cuda), plan, out=Y)
+                assert rel_err(Y, ref) < TOL, (d, seg_len, bins, unroll)
                 assert float(Y[n - 5:].abs().max()) == 0.0          # empty rows are zeros
     finally:
         _lib.set_tuning("spmm_rows_per_warp", 1)

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--caches", type=str, default="0,1")
     ap.add_argument("--variants", type=str, default="0")
     ap.add_argument("--unrolls", type=str, default="4,8")
+    ap.add_argument("--bins", type=str, default="1")
     ap.add_argument("--stages", type=str, default="2,3,4")
     ap.add_argument("--out", type=str, default="")
     args = ap.parse_args()
@@ -96,7 +97,9 @@ def main():
         _lib.set_tuning("spmm_variant", 0)
         if "0" not in args.variants.split(","):
             continue
-        for block, unroll, cache, rpw in itertools.product(blocks, unrolls, caches, (1, 2)):
+        for block, unroll, cache, rpw, bins in itertools.product(blocks, unrolls, caches, (1, 2),
+                                                                 [int(b) for b in args.bins.split(",")]):
+            _lib.set_tuning("spmm_bins", bins)
             _lib.set_tuning("spmm_block", block)
             _lib.set_tuning("spmm_unroll", unroll)
             _lib.set_tuning("spmm_cache", cache)
@@ -105,7 +108,7 @@ def main():
             if ref is None:
                 ref = Y.clone()
             err = float((Y - ref).abs().max())
-            r = {"seg_len": seg, "block": block, "unroll": unroll, "cache": cache, "rows_per_warp": rpw, "ms": ms,
+            r = {"seg_len": seg, "block": block, "unroll": unroll, "cache": cache, "rows_per_warp": rpw, "bins": bins, "ms": ms,
                  "alg_GBps": alg / ms / 1e6, "maxdiff_vs_first": err}
             results.append(r)
             print(json.dumps(r), flush=True)
