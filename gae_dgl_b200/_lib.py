@@ -68,6 +68,8 @@ SIGNATURES = {
     "gae_decoder_logits_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "gae_in_degrees_i64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gae_batch_offset_cols_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "gae_batch_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "gae_gather_rows_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "gae_pull_rows_p2p_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64,
                                       c_void_p]),

@@ -85,6 +85,49 @@ __global__ void batch_offset_cols_kernel(int32_t *__restrict__ col, const int64_
     col[e] += (int32_t)node_off[lo];
 }
 
+// dgl.batch on device from a PACKED dataset (all member graphs resident in HBM as one CSR with
+// graph-local column ids): assemble the block-diagonal union of graphs gid[0..K) -- row
+// pointers, columns (+ node offset) and node features -- with no host loop over the members.
+__device__ __forceinline__ int64_t find_segment(const int64_t *__restrict__ off, int64_t k_count, int64_t x) {
+    int64_t lo = 0, hi = k_count;   // off[lo] <= x < off[lo+1]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void batch_assemble_kernel(const int64_t *__restrict__ rowptr_all, const int32_t *__restrict__ col_all,
+                                      const int64_t *__restrict__ node_ptr, const int64_t *__restrict__ gid,
+                                      int64_t K, const int64_t *__restrict__ noff, const int64_t *__restrict__ eoff,
+                                      int64_t n_out, int64_t e_out, int64_t *__restrict__ out_rowptr,
+                                      int32_t *__restrict__ out_col) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_out) {
+        const int64_t k = find_segment(noff, K, t);
+        const int64_t base = node_ptr[gid[k]];
+        const int64_t src = base + (t - noff[k]);
+        out_rowptr[t + 1] = eoff[k] + (rowptr_all[src + 1] - rowptr_all[base]);
+        if (t == 0) out_rowptr[0] = 0;
+    }
+    if (t < e_out) {
+        const int64_t k = find_segment(eoff, K, t);
+        const int64_t e_src = rowptr_all[node_ptr[gid[k]]] + (t - eoff[k]);
+        out_col[t] = col_all[e_src] + (int32_t)noff[k];
+    }
+}
+
+__global__ void batch_features_kernel(const float *__restrict__ feat_all, int64_t ldf, const int64_t *__restrict__ node_ptr,
+                                      const int64_t *__restrict__ gid, int64_t K, const int64_t *__restrict__ noff,
+                                      int64_t n_out, int d, float *__restrict__ out, int64_t ldo) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t node = t / d;
+    const int c = (int)(t % d);
+    if (node >= n_out) return;
+    const int64_t k = find_segment(noff, K, node);
+    out[node * ldo + c] = __ldg(feat_all + (node_ptr[gid[k]] + (node - noff[k])) * ldf + c);
+}
+
 // pack rows idx[] of X (128-bit when aligned, one lane group per row)
 template <bool VEC>
 __global__ void gather_rows_kernel(const float *__restrict__ X, int64_t ldx, const int64_t *__restrict__ idx,
@@ -206,6 +249,33 @@ extern "C" int gae_batch_offset_cols_i32(int32_t *col_cat, const int64_t *edge_g
     batch_offset_cols_kernel<<<(unsigned)cdiv(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
         col_cat, edge_graph_ptr, node_off, n_graphs, n_edges);
     GAE_LAUNCH_CHECK();
+    return GAE_OK;
+}
+
+extern "C" int gae_batch_assemble(const int64_t *rowptr_all, const int32_t *col_all, const int64_t *node_ptr,
+                                  const int64_t *gid, int64_t n_graphs, const int64_t *node_off,
+                                  const int64_t *edge_off, int64_t n_out, int64_t e_out, int64_t *out_rowptr,
+                                  int32_t *out_col, const float *feat_all, int64_t ldf, int32_t d, float *out_feat,
+                                  int64_t ld_out, void *stream) {
+    GAE_CHECK_ARG(n_graphs > 0 && n_out >= 0 && e_out >= 0, "bad sizes");
+    GAE_CHECK_ARG(rowptr_all && node_ptr && gid && node_off && edge_off && out_rowptr, "null pointer");
+    GAE_CHECK_ARG(e_out == 0 || (col_all && out_col), "null column arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t work = n_out > e_out ? n_out : e_out;
+    if (work > 0) {
+        batch_assemble_kernel<<<(unsigned)cdiv(work, 256), 256, 0, st>>>(rowptr_all, col_all, node_ptr, gid, n_graphs,
+                                                                          node_off, edge_off, n_out, e_out, out_rowptr,
+                                                                          out_col);
+        GAE_LAUNCH_CHECK();
+    } else {
+        GAE_CUDA(cudaMemsetAsync(out_rowptr, 0, sizeof(int64_t), st));
+    }
+    if (feat_all && out_feat && n_out > 0 && d > 0) {
+        GAE_CHECK_ARG(ldf >= d && ld_out >= d, "feature leading dimension too small");
+        batch_features_kernel<<<(unsigned)cdiv(n_out * d, 256), 256, 0, st>>>(feat_all, ldf, node_ptr, gid, n_graphs,
+                                                                               node_off, n_out, d, out_feat, ld_out);
+        GAE_LAUNCH_CHECK();
+    }
     return GAE_OK;
 }
 

@@ -437,3 +437,101 @@ def batch(graphs: Sequence[DGLGraph], device=None) -> DGLGraph:
     for k in keys:
         bg.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0).to(device)
     return bg
+
+
+class PackedGraphDataset:
+    """All graphs of a dataset resident on the device as ONE packed CSR (+ its transpose + node
+    features), so a mini-batch is assembled by a kernel instead of a host loop over its members
+    (after fusing the decoder, `collate` on the Python main thread
+    -- train_inductive.py:31-35,84 -- becomes the bottleneck of the inductive loop).
+
+    `batch(ids)` returns the same block-diagonal DGLGraph as `batch([graphs[i] for i in ids])`,
+    bit-identical indexing (tested), with ndata[feature_key] gathered on the device."""
+
+    def __init__(self, graphs: Sequence[DGLGraph], device, feature_key: str = "h"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise GaeError("PackedGraphDataset lives on a CUDA device")
+        self.feature_key = feature_key
+        self.n_graphs = len(graphs)
+        nodes = np.asarray([g.number_of_nodes() for g in graphs], dtype=np.int64)
+        self.nodes = nodes
+        self.node_ptr_host = np.zeros(len(graphs) + 1, dtype=np.int64)
+        np.cumsum(nodes, out=self.node_ptr_host[1:])
+        self._seg_len = graphs[0]._seg_len if graphs else ops.DEFAULT_SEG_LEN
+
+        def pack(get):
+            parts = [get(g) for g in graphs]
+            edges = np.asarray([p[1].size for p in parts], dtype=np.int64)
+            eptr = np.zeros(len(graphs) + 1, dtype=np.int64)
+            np.cumsum(edges, out=eptr[1:])
+            rowptr = np.zeros(int(self.node_ptr_host[-1]) + 1, dtype=np.int64)
+            pos = 1
+            for k, (rp, _) in enumerate(parts):
+                m = rp.size - 1
+                rowptr[pos:pos + m] = rp[1:] + eptr[k]
+                pos += m
+            col = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int32)
+            return edges, torch.from_numpy(rowptr).to(self.device), torch.from_numpy(col).to(self.device)
+
+        self.edges, self.rowptr_all, self.col_all = pack(DGLGraph.host_csr)
+        self.edges_t, self.rowptr_all_t, self.col_all_t = pack(DGLGraph.host_csr_t)
+        self.node_ptr = torch.from_numpy(self.node_ptr_host).to(self.device)
+        feats = [g.ndata[feature_key] for g in graphs] if graphs and feature_key in graphs[0].ndata else None
+        self.feat_all = ops.as_rows(torch.cat(feats, 0).to(self.device, torch.float32), "features") if feats else None
+
+    def __len__(self):
+        return self.n_graphs
+
+    def batch(self, ids) -> DGLGraph:
+        import ctypes
+        from . import _lib
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        k = ids.size
+        if k == 0:
+            raise GaeError("batch() needs at least one graph")
+        noff = np.zeros(k + 1, dtype=np.int64)
+        np.cumsum(self.nodes[ids], out=noff[1:])
+        n_out = int(noff[-1])
+        lib = _lib.load()
+        dev = self.device
+        # ONE truly asynchronous H2D for all index vectors: they are staged in pinned memory
+        # (a pageable source would make cudaMemcpyAsync synchronise the stream every batch)
+        eoffs = []
+        for edges in (self.edges, self.edges_t):
+            eoff = np.zeros(k + 1, dtype=np.int64)
+            np.cumsum(edges[ids], out=eoff[1:])
+            eoffs.append(eoff)
+        staged = torch.from_numpy(np.concatenate([ids, noff, eoffs[0], eoffs[1]])).pin_memory()
+        on_dev = staged.to(dev, non_blocking=True)
+        gid_dev, noff_dev = on_dev[:k], on_dev[k:2 * k + 1]
+        eoff_devs = (on_dev[2 * k + 1:3 * k + 2], on_dev[3 * k + 2:4 * k + 3])
+        bg = DGLGraph(seg_len=self._seg_len)
+        bg._n = n_out
+        bg._device = dev
+        bg.batch_num_nodes = self.nodes[ids].tolist()
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        out = []
+        for which, (rowptr_all, col_all, with_feat) in enumerate(((self.rowptr_all, self.col_all, True),
+                                                                  (self.rowptr_all_t, self.col_all_t, False))):
+            eoff, eoff_dev = eoffs[which], eoff_devs[which]
+            e_out = int(eoff[-1])
+            rp = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
+            col = torch.empty(e_out, dtype=torch.int32, device=dev)
+            feat_out = None
+            if with_feat and self.feat_all is not None:
+                feat_out = ops.alloc_rows(n_out, self.feat_all.shape[1], dev)
+            rc = lib.gae_batch_assemble(p(rowptr_all), p(col_all), p(self.node_ptr), p(gid_dev), k, p(noff_dev),
+                                        p(eoff_dev), n_out, e_out, p(rp), p(col),
+                                        p(self.feat_all) if feat_out is not None else None,
+                                        self.feat_all.stride(0) if feat_out is not None else 0,
+                                        self.feat_all.shape[1] if feat_out is not None else 0, p(feat_out),
+                                        feat_out.stride(0) if feat_out is not None else 0,
+                                        torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "gae_batch_assemble")
+            if feat_out is not None:
+                bg.ndata[self.feature_key] = feat_out
+            out.append(CSR(rp, col, None))
+        bg._dev_csr, bg._dev_csr_t = out
+        bg._frozen_edges = int(out[0].col.numel())
+        return bg

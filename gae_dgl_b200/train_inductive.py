@@ -42,6 +42,9 @@ def build_parser():
     parser.add_argument('--variational', action='store_true', help='train VGAE instead of GAE')
     parser.add_argument('--dense_decoder', action='store_true', help="reference's materialised N x N loss")
     parser.add_argument('--resume', type=str, default=None, help='checkpoint (ep{NN}.pkl or .ckpt) to resume from')
+    parser.add_argument('--host_collate', action='store_true',
+                        help='collate each batch from the member graphs on the host (reference flow) instead of the '
+                             'device-resident packed dataset')
     return parser
 
 
@@ -146,9 +149,18 @@ def main(argv=None):
     val_dataset = MolDataset(val_graphs)
     del train_graphs, val_graphs
 
-    collate = make_collate(device)
-    train_loader = DataLoader(train_dataset, batch_size=args.batch_size, shuffle=True, collate_fn=collate)
-    val_loader = DataLoader(val_dataset, batch_size=args.batch_size, shuffle=False, collate_fn=collate)
+    if args.host_collate:
+        collate = make_collate(device)
+        train_loader = DataLoader(train_dataset, batch_size=args.batch_size, shuffle=True, collate_fn=collate)
+        val_loader = DataLoader(val_dataset, batch_size=args.batch_size, shuffle=False, collate_fn=collate)
+    else:
+        # dgl.batch on device: both splits live in HBM as packed CSRs; a batch is one kernel
+        train_packed = dgl.PackedGraphDataset(train_dataset.graphs, device)
+        val_packed = dgl.PackedGraphDataset(val_dataset.graphs, device)
+        train_loader = DataLoader(range(len(train_dataset)), batch_size=args.batch_size, shuffle=True,
+                                  collate_fn=train_packed.batch)
+        val_loader = DataLoader(range(len(val_dataset)), batch_size=args.batch_size, shuffle=False,
+                                collate_fn=val_packed.batch)
     trainer = Trainer(model, args, device)
     start_epoch = trainer.load(args.resume) if args.resume else 0
     train_losses, val_losses = [], []

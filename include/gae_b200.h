@@ -174,6 +174,18 @@ int gae_batch_offset_cols_i32(int32_t *col_cat, const int64_t *edge_graph_ptr,
                               const int64_t *node_off, int64_t n_graphs, int64_t n_edges,
                               void *stream);
 
+/* dgl.batch from a PACKED dataset (8f rank 1): every member graph is resident in HBM inside one
+ * CSR (rowptr_all int64 over all nodes with global edge offsets, col_all int32 with graph-LOCAL
+ * source ids, node_ptr [G+1] node prefix sums, feat_all [sum n, ldf]).  Builds the union of graphs
+ * gid[0..n_graphs): out_rowptr [n_out+1], out_col [e_out] (+ node offsets), out_feat [n_out, ld_out]
+ * (feat_all / out_feat may be NULL).  node_off / edge_off [n_graphs+1] are the prefix sums of the
+ * selected graphs' node / edge counts (device). */
+int gae_batch_assemble(const int64_t *rowptr_all, const int32_t *col_all, const int64_t *node_ptr,
+                       const int64_t *gid, int64_t n_graphs, const int64_t *node_off,
+                       const int64_t *edge_off, int64_t n_out, int64_t e_out,
+                       int64_t *out_rowptr, int32_t *out_col, const float *feat_all, int64_t ldf,
+                       int32_t d, float *out_feat, int64_t ld_out, void *stream);
+
 /* ---- K7: halo exchange helpers (8e) -------------------------------------------------------- */
 /* Pack rows idx[0..m) of X into out (send buffer of the all-to-all-v). */
 int gae_gather_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t m, int32_t d,
