@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgae_b200.so")
@@ -65,6 +65,10 @@ SIGNATURES = {
     "gae_decoder_ws_bytes": (c_int64, [c_int64, c_int32]),
     "gae_decoder_bce_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_float, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "gae_decoder_blockdiag_ws_bytes": (c_int64, [c_int64, c_int32]),
+    "gae_decoder_bce_blockdiag_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_double, c_float, c_int32, c_void_p, c_void_p,
+                                              c_int64, c_void_p, c_int64, c_void_p]),
     "gae_decoder_logits_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "gae_in_degrees_i64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gae_batch_offset_cols_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

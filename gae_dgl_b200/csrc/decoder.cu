@@ -167,7 +167,8 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
                     const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                     const int64_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t, float pw,
                     const float *__restrict__ dz_part, int splits, int mode, float inv_n2,
-                    float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part) {
+                    float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part,
+                    const int64_t *__restrict__ blk_lo, const int64_t *__restrict__ blk_hi) {
     constexpr int LPR = D / 4;
     constexpr int RPB = 256 / LPR;
     __shared__ double red[8];
@@ -196,13 +197,32 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
 
     const float4 zi = valid ? load_row(i) : f4_zero();
     float4 g = f4_zero();
-    if (want_grad && valid) {
+    if (want_grad && valid && !blk_lo) {
         for (int s = 0; s < splits; ++s)
             f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
         // x_ij = x_ji: (G + G^T) Zd doubles the dense term
         g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
     }
     float lsum = 0.f;
+    if (blk_lo) {
+        // block-diagonal variant (per-graph decoder): the dense term runs
+        // over the row's own graph only, j in [blk_lo[i], blk_hi[i]); no dense pass was launched
+        const int64_t j0 = valid ? blk_lo[i] : 0, j1 = valid ? blk_hi[i] : 0;
+        int64_t len = j1 - j0, maxlen = len;
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
+        for (int64_t t = 0; t < maxlen; ++t) {
+            const bool on = t < len;
+            const float4 zj = on ? load_row(j0 + t) : f4_zero();
+            const float x = group_dot(zi, zj);
+            float l, sg;
+            softplus_parts(x, l, sg);
+            if (on) {
+                lsum += fmaxf(x, 0.f) + l;
+                f4_fma(g, 2.f * sg, zj);            // (G + G^T) Zd with x_ij = x_ji
+            }
+        }
+    }
     // groups of one warp walk different rows: loop to the warp-wide max degree so the
     // shuffles inside group_dot stay convergent
     {
@@ -375,17 +395,67 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     const float inv_n2 = (float)(1.0 / ((double)n * (double)n));
     if (c.D == 16)
         dec_finalize_kernel<16><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
+                                                                        nullptr, nullptr);
     else if (c.D == 32)
         dec_finalize_kernel<32><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
+                                                                        nullptr, nullptr);
     else
         dec_finalize_kernel<64><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
+                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
+                                                                        nullptr, nullptr);
     GAE_LAUNCH_CHECK();
     if (want_loss) {
         dec_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, c.nb * c.splits + c.fin_blocks,
                                                   1.0 / ((double)n * (double)n), loss);
+        GAE_LAUNCH_CHECK();
+    }
+    return GAE_OK;
+}
+
+extern "C" int64_t gae_decoder_blockdiag_ws_bytes(int64_t n, int32_t d) {
+    DecConfig c;
+    if (n <= 0 || d <= 0 || !dec_config(n, d, &c)) return 0;
+    return align_up((int64_t)sizeof(double) * c.fin_blocks, 256);
+}
+
+extern "C" int gae_decoder_bce_blockdiag_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, const int64_t *rowptr,
+                                             const int32_t *col, const int64_t *rowptr_t, const int32_t *col_t,
+                                             const int64_t *blk_lo, const int64_t *blk_hi, double n_pairs,
+                                             float pos_weight, int32_t mode, float *loss, float *dZd_unit,
+                                             int64_t ld_dz, void *ws, int64_t ws_bytes, void *stream) {
+    GAE_CHECK_ARG(n > 0 && d > 0 && n_pairs > 0, "n, d, n_pairs must be > 0");
+    GAE_CHECK_ARG(Zd && rowptr && blk_lo && blk_hi, "null pointer");
+    GAE_CHECK_ARG(ldz >= d, "ldz too small");
+    GAE_CHECK_ARG((mode & ~3) == 0 && mode != 0, "mode must be a combination of GAE_DEC_LOSS|GAE_DEC_GRAD");
+    const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
+    GAE_CHECK_ARG(!want_loss || loss, "loss pointer required");
+    GAE_CHECK_ARG(!want_grad || (dZd_unit && rowptr_t && ld_dz >= d), "gradient needs dZd_unit and CSR(A^T)");
+    DecConfig c;
+    if (!dec_config(n, d, &c)) {
+        set_error("decoder supports embedding width d <= 64 (got %d)", d);
+        return GAE_ERR_UNSUPPORTED;
+    }
+    if (!ws || ws_bytes < gae_decoder_blockdiag_ws_bytes(n, d)) {
+        set_error("decoder workspace too small");
+        return GAE_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *loss_part = (double *)ws;
+    const float inv = (float)(1.0 / n_pairs);
+    if (c.D == 16)
+        dec_finalize_kernel<16><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        nullptr, 0, mode, inv, dZd_unit, ld_dz, loss_part, blk_lo, blk_hi);
+    else if (c.D == 32)
+        dec_finalize_kernel<32><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        nullptr, 0, mode, inv, dZd_unit, ld_dz, loss_part, blk_lo, blk_hi);
+    else
+        dec_finalize_kernel<64><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
+                                                                        nullptr, 0, mode, inv, dZd_unit, ld_dz, loss_part, blk_lo, blk_hi);
+    GAE_LAUNCH_CHECK();
+    if (want_loss) {
+        dec_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, c.fin_blocks, 1.0 / n_pairs, loss);
         GAE_LAUNCH_CHECK();
     }
     return GAE_OK;

@@ -105,19 +105,24 @@ class InnerProductDecoder(nn.Module):
         x = ops.DecoderLogitsFunction.apply(z, float(self.dropout), mask, st)
         return self.activation(x)
 
-    def loss(self, z, g: DGLGraph, pos_weight: float, mask: Optional[torch.Tensor] = None):
+    def loss(self, z, g: DGLGraph, pos_weight: float, mask: Optional[torch.Tensor] = None, per_graph: bool = False):
         """Fused path: mean BCE-with-logits(z_d z_d^T, A, pos_weight) without the N x N arrays
-        (replaces gae.py:71 + train_inductive.py:44,48)."""
+        (replaces gae.py:71 + train_inductive.py:44,48).  per_graph=True restricts the pairs to
+        each member graph of a batch (block-diagonal; an extension, not the reference default)."""
         st = None if mask is not None else self._rng_state(z.device)
-        return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, st)
+        return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, st, per_graph)
 
 
-def pos_weight_of(g: DGLGraph, transductive: bool = False) -> float:
+def pos_weight_of(g: DGLGraph, transductive: bool = False, per_graph: bool = False) -> float:
     """train_inductive.py:46 / train_transductive.py:60 evaluated from integers: the sum of the
     dense adjacency equals the edge count (with multiplicity), exactly representable in fp32
-    below 2^24 edges; the arithmetic below repeats the reference's fp32 tensor ops."""
+    below 2^24 edges; the arithmetic below repeats the reference's fp32 tensor ops.
+    per_graph: the pair count is sum_k n_k^2 (block-diagonal decoder) instead of N^2."""
     n = g.number_of_nodes()
     adj_sum = torch.tensor(float(g.number_of_edges()), dtype=torch.float32)
+    if per_graph:
+        pairs = g.block_ranges()[2]
+        return float((pairs - adj_sum) / adj_sum)
     if transductive:
         return float(torch.Tensor([float(n * n - adj_sum) / adj_sum])[0])
     return float((n * n - adj_sum) / adj_sum)
@@ -146,14 +151,14 @@ class GAE(nn.Module):
         return h
 
     def loss(self, g, pos_weight: Optional[float] = None, mask: Optional[torch.Tensor] = None,
-             transductive: bool = False):
+             transductive: bool = False, per_graph: bool = False):
         """Fused equivalent of `BCELoss(model.forward(g), adj, pos_weight)`
         (train_inductive.py:44-48), including the gae.py:53 write-back."""
         h = self.encode(g)
         g.ndata['h'] = h
         if pos_weight is None:
-            pos_weight = pos_weight_of(g, transductive)
-        return self.decoder.loss(h, g, pos_weight, mask)
+            pos_weight = pos_weight_of(g, transductive, per_graph)
+        return self.decoder.loss(h, g, pos_weight, mask, per_graph)
 
     reconstruction_loss = loss
 

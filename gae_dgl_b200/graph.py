@@ -273,6 +273,21 @@ class DGLGraph:
                 self._dev_csr_t = self._make_dev(self.host_csr_t())
         return self._dev_csr_t
 
+    def block_ranges(self):
+        """(blk_lo int64 [N], blk_hi int64 [N], sum_k n_k^2) of the member graphs of a batched
+        graph (a plain graph is one block) -- input of the per-graph decoder."""
+        cached = getattr(self, "_block_ranges", None)
+        if cached is not None and cached[0].device == self._device:
+            return cached
+        sizes = self.batch_num_nodes if self.batch_num_nodes else [self._n]
+        sz = torch.tensor(sizes, dtype=torch.int64)
+        hi = torch.cumsum(sz, 0)
+        lo = hi - sz
+        out = (torch.repeat_interleave(lo, sz).to(self._device), torch.repeat_interleave(hi, sz).to(self._device),
+               float((sz.double() ** 2).sum()))
+        self._block_ranges = out
+        return out
+
     def in_degrees(self) -> torch.Tensor:
         """train_transductive.py:55 -- int64 in-degree per node."""
         c = self.csr()

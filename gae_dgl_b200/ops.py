@@ -278,6 +278,27 @@ def decoder_bce(Zd: torch.Tensor, rowptr, col, rowptr_t, col_t, pos_weight: floa
     return loss, dZ
 
 
+def decoder_bce_blockdiag(Zd: torch.Tensor, rowptr, col, rowptr_t, col_t, blk_lo, blk_hi, n_pairs: float,
+                          pos_weight: float, want_loss=True, want_grad=False):
+    """Per-graph (block-diagonal) fused decoder + BCE for batched graphs."""
+    Zd = as_rows(Zd, "Zd")
+    n, d = Zd.shape
+    lib = _lib.load()
+    ws_bytes = lib.gae_decoder_blockdiag_ws_bytes(n, d)
+    if ws_bytes <= 0:
+        raise GaeError(f"decoder does not support n={n}, d={d} (d must be <= 64)")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Zd.device)
+    loss = torch.empty((), dtype=torch.float32, device=Zd.device) if want_loss else None
+    dZ = alloc_rows(n, d, Zd.device) if want_grad else None
+    mode = (DEC_LOSS if want_loss else 0) | (DEC_GRAD if want_grad else 0)
+    rc = lib.gae_decoder_bce_blockdiag_f32(_ptr(Zd), _ld(Zd), n, d, _ptr(rowptr), _ptr(col), _ptr(rowptr_t), _ptr(col_t),
+                                           _ptr(blk_lo), _ptr(blk_hi), float(n_pairs), float(pos_weight), mode,
+                                           _ptr(loss), _ptr(dZ), _ld(dZ) if dZ is not None else 0, _ptr(ws), ws_bytes,
+                                           _stream())
+    _lib.check(rc, "gae_decoder_bce_blockdiag_f32")
+    return loss, dZ
+
+
 def decoder_logits(Zd: torch.Tensor) -> torch.Tensor:
     Zd = as_rows(Zd, "Zd")
     n, d = Zd.shape
@@ -350,12 +371,17 @@ class DecoderLossFunction(torch.autograd.Function):
     produced in the same pass as the loss and scaled by grad_output in backward."""
 
     @staticmethod
-    def forward(ctx, Z, graph, pos_weight, p, mask, rng_state):
+    def forward(ctx, Z, graph, pos_weight, p, mask, rng_state, per_graph=False):
         csr, csr_t = graph.csr(), graph.csr_t()
         need_grad = Z.requires_grad
         Zd, m = dropout_fwd(Z, p, mask, rng_state=rng_state)
-        loss, dZd_unit = decoder_bce(Zd, csr.rowptr, csr.col, csr_t.rowptr, csr_t.col, pos_weight,
-                                     want_loss=True, want_grad=need_grad)
+        if per_graph:
+            lo, hi, n_pairs = graph.block_ranges()
+            loss, dZd_unit = decoder_bce_blockdiag(Zd, csr.rowptr, csr.col, csr_t.rowptr, csr_t.col, lo, hi, n_pairs,
+                                                   pos_weight, want_loss=True, want_grad=need_grad)
+        else:
+            loss, dZd_unit = decoder_bce(Zd, csr.rowptr, csr.col, csr_t.rowptr, csr_t.col, pos_weight,
+                                         want_loss=True, want_grad=need_grad)
         ctx.p = p
         ctx.mask = m
         ctx.dZd_unit = dZd_unit
@@ -364,9 +390,9 @@ class DecoderLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         if ctx.dZd_unit is None:
-            return (None,) * 6
+            return (None,) * 7
         dZ = dropout_bwd(ctx.dZd_unit, ctx.mask, ctx.p, grad_scale=g)
-        return dZ, None, None, None, None, None
+        return dZ, None, None, None, None, None, None
 
 
 class DecoderLogitsFunction(torch.autograd.Function):

@@ -42,6 +42,8 @@ def build_parser():
     parser.add_argument('--variational', action='store_true', help='train VGAE instead of GAE')
     parser.add_argument('--dense_decoder', action='store_true', help="reference's materialised N x N loss")
     parser.add_argument('--resume', type=str, default=None, help='checkpoint (ep{NN}.pkl or .ckpt) to resume from')
+    parser.add_argument('--per_graph_decoder', action='store_true',
+                        help='decode each molecule separately (block-diagonal pairs) instead of the full batch matrix')
     parser.add_argument('--host_collate', action='store_true',
                         help='collate each batch from the member graphs on the host (reference flow) instead of the '
                              'device-resident packed dataset')
@@ -60,11 +62,12 @@ class Trainer:
         self.device = device if device is not None else next(model.parameters()).device
         self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr)
         self.dense = bool(getattr(args, 'dense_decoder', False))
+        self.per_graph = bool(getattr(args, 'per_graph_decoder', False))
         print('Total Parameters:', sum([p.nelement() for p in self.model.parameters()]))
 
     def loss(self, g):
         if not self.dense:
-            return self.model.loss(g)                       # fused K5/K6
+            return self.model.loss(g, per_graph=self.per_graph)     # fused K5/K6
         adj = g.adjacency_matrix().to_dense().to(self.device)     # train_inductive.py:44
         pos_weight = ((adj.shape[0] * adj.shape[0] - adj.sum()) / adj.sum())   # :46
         adj_logits = self.model.forward(g)                  # :47

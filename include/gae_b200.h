@@ -159,6 +159,16 @@ int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d,
                         const int32_t *col_t, float pos_weight, int32_t mode, float *loss,
                         float *dZd_unit, int64_t ld_dz, void *ws, int64_t ws_bytes,
                         void *stream);
+/* Block-diagonal variant for batched graphs (NOT the reference default, which
+ * decodes the full (sum n_k)^2 matrix including cross-molecule negatives, train_inductive.py:44-48):
+ * the pair sum runs over j in [blk_lo[i], blk_hi[i]) only, normalised by n_pairs = sum_k n_k^2. */
+int64_t gae_decoder_blockdiag_ws_bytes(int64_t n, int32_t d);
+int gae_decoder_bce_blockdiag_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d,
+                                  const int64_t *rowptr, const int32_t *col,
+                                  const int64_t *rowptr_t, const int32_t *col_t,
+                                  const int64_t *blk_lo, const int64_t *blk_hi, double n_pairs,
+                                  float pos_weight, int32_t mode, float *loss, float *dZd_unit,
+                                  int64_t ld_dz, void *ws, int64_t ws_bytes, void *stream);
 /* Materialised logits X = Zd Zd^T [n,n] (the value GAE.forward returns, gae.py:54-55). */
 int gae_decoder_logits_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, float *X,
                            int64_t ldx, void *stream);

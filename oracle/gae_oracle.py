@@ -209,6 +209,20 @@ def bce_loss_sparse_form(zd: torch.Tensor, rowptr, col, pos_weight: float) -> to
     return (dense + sparse) / float(n * n)
 
 
+def bce_loss_blockdiag(zd: torch.Tensor, adj: torch.Tensor, sizes: Sequence[int], pos_weight: float) -> torch.Tensor:
+    """Per-graph variant (not in the reference): the element-wise weighted
+    BCE of train_inductive.py:48 summed over the diagonal blocks only, divided by sum_k n_k^2."""
+    total, pairs, lo = zd.new_zeros(()), 0, 0
+    pw = torch.as_tensor(pos_weight, dtype=zd.dtype)
+    for n_k in sizes:
+        hi = lo + n_k
+        x = zd[lo:hi] @ zd[lo:hi].t()
+        total = total + F.binary_cross_entropy_with_logits(x, adj[lo:hi, lo:hi], pos_weight=pw, reduction="sum")
+        pairs += n_k * n_k
+        lo = hi
+    return total / pairs
+
+
 def train_step(rowptr, col, X, weights, keep_mask, p=0.1, transductive=False, dtype=torch.float32):
     """One full forward + backward of the reference step (train_inductive.py:44-51).
     Returns (loss, embeddings, [grad W, grad b per layer]).  ``weights`` are (W, b) pairs;

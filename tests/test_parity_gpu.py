@@ -463,3 +463,36 @@ def test_packed_dataset_batch_is_bit_identical_to_host_collation(cuda):
     l1 = model.loss(packed.batch(ids), mask=mask)
     l2 = model.loss(G.batch([ds[i] for i in ids], device=cuda), mask=mask)
     assert float(l1) == float(l2)
+
+
+def test_per_graph_decoder_parity(cuda):
+    """Block-diagonal decoder (8f rank 2) vs the oracle's per-block BCE, loss and gradients."""
+    ds = synthetic.zinc_like_dataset(40, seed=4)
+    bg = G.batch(ds, device=cuda)
+    n = bg.number_of_nodes()
+    sizes = bg.batch_num_nodes
+    rowptr, col = bg.csr().rowptr.cpu(), bg.csr().col.cpu()
+    adj = O.dense_adj_from_csr(rowptr, col, torch.float64)
+    pw = G.pos_weight_of(bg, per_graph=True)
+    assert abs(pw - (sum(s * s for s in sizes) - bg.number_of_edges()) / bg.number_of_edges()) < 1e-4 * pw
+    g = torch.Generator().manual_seed(0)
+    Z = 0.7 * torch.randn(n, 16, generator=g)
+    mask = torch.rand(n, 16, generator=g) >= 0.1
+    Zr = Z.double().requires_grad_(True)
+    ref = O.bce_loss_blockdiag(O.apply_dropout_mask(Zr, mask, 0.1), adj, sizes, pw)
+    ref.backward()
+    Zc = Z.to(cuda).requires_grad_(True)
+    dec = G.InnerProductDecoder(activation=lambda x: x)
+    loss = dec.loss(Zc, bg, pw, mask=mask.to(cuda), per_graph=True)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert float((Zc.grad.double().cpu() - Zr.grad).abs().max()) < TOL * float(Zr.grad.abs().max())
+    # a single graph is one block: per_graph == full decoder
+    g1, X1 = synthetic.planetoid_like("cora", seed=3)
+    g1.to(cuda)
+    Z1 = (0.3 * torch.randn(2708, 16, generator=g)).to(cuda)
+    m1 = (torch.rand(2708, 16, generator=g) >= 0.1).to(cuda)
+    pw1 = G.pos_weight_of(g1)
+    a = dec.loss(Z1, g1, pw1, mask=m1, per_graph=True)
+    b = dec.loss(Z1, g1, pw1, mask=m1)
+    assert abs(float(a) - float(b)) < TOL * abs(float(b))
