@@ -30,7 +30,7 @@ struct DecConfig {
 };
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
-    if (d <= 16) { c->D = 16; c->R = 2; }
+    if (d <= 16) { c->D = 16; c->R = tuning(T_DEC_ROWS) == 1 ? 1 : 2; }
     else if (d <= 32) { c->D = 32; c->R = 1; }
     else if (d <= 64) { c->D = 64; c->R = 1; }
     else return false;
@@ -42,7 +42,7 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (want <= 0) {
         // ~3 waves of CTAs (4 resident 128-thread CTAs per SM at 128 registers), then nudge the
         // split count so the last wave is full: wave quantisation cost 20 % at Pubmed size
-        const int64_t slots = 148 * 4;
+        const int64_t slots = 148 * ((c->D == 16 && c->R == 1) ? 8 : 4);
         want = cdiv(slots * 3, c->nb);
         double best = 1e30;
         int64_t best_s = want;
@@ -66,7 +66,7 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
 }
 
 template <int D, int R, bool LOSS, bool GRAD>
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, (D == 16 && R == 1) ? 8 : 1)
 dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
                  float *__restrict__ dz_part, double *__restrict__ loss_part) {
     constexpr int JT = 2048 / D;
@@ -388,7 +388,8 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     double *loss_part = (double *)((char *)ws + align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256));
     double *loss_part_edges = loss_part + c.nb * c.splits;
 
-    if (c.D == 16) GAE_CUDA((launch_dense<16, 2>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
+    if (c.D == 16 && c.R == 1) GAE_CUDA((launch_dense<16, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
+    else if (c.D == 16) GAE_CUDA((launch_dense<16, 2>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
     else if (c.D == 32) GAE_CUDA((launch_dense<32, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
     else GAE_CUDA((launch_dense<64, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
 

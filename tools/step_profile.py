@@ -70,7 +70,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--which", type=str, default="pubmed,zinc,cora")
+    ap.add_argument("--tune", type=str, default="")
     args = ap.parse_args()
+    from gae_dgl_b200 import _lib
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        _lib.set_tuning(k, int(v))
     if "pubmed" in args.which:
         g, X = synthetic.planetoid_like("pubmed", seed=0)
         run("pubmed", g, X, 500, 1e-2, args.steps, True)
