@@ -496,3 +496,44 @@ def test_per_graph_decoder_parity(cuda):
     a = dec.loss(Z1, g1, pw1, mask=m1, per_graph=True)
     b = dec.loss(Z1, g1, pw1, mask=m1)
     assert abs(float(a) - float(b)) < TOL * abs(float(b))
+
+
+def test_spmm_full_size_c4_properties(cuda):
+    """BASELINE.json configs[3] at FULL size (R-MAT scale 22, 1e8 edges, d = 64): size-independent
+    properties (ones -> in-degrees exactly, adjoint identity, determinism) plus the oracle on a
+    random sample of rows (the fp64 C loop restricted to those rows)."""
+    scale, e, d = 22, 100_000_000, 64
+    n = 1 << scale
+    src, dst = synthetic.rmat_edges(scale, e, seed=1, device=cuda)
+    rowptr, col = G.graph.coo_to_csr_torch(src, dst, n)
+    rowptr_t, col_t = G.graph.coo_to_csr_torch(dst, src, n)
+    del src, dst
+    g = G.DGLGraph.from_csr(rowptr, col, csr_t=(rowptr_t, col_t))
+    c, t = g.csr(), g.csr_t()
+    assert c.plan.bins is not None and c.plan.n_long > 0
+    st = c.plan.struct
+    assert st.n_empty + st.n_short + st.n_mid + c.plan.n_long == n          # every row in exactly one class
+    deg = g.in_degrees()
+    assert int(deg.sum()) == e and int(rowptr[-1]) == e
+    ones = torch.ones(n, d, device=cuda)
+    Y1 = ops.spmm(c.rowptr, c.col, ones, c.plan)
+    assert torch.equal(Y1[:, 0], deg.float()) and torch.equal(Y1[:, d - 1], deg.float())
+    del ones, Y1
+    X = synthetic.hashed_normal(n, d, 2, device=cuda)
+    Z = synthetic.hashed_normal(n, d, 3, device=cuda)
+    Y = ops.spmm(c.rowptr, c.col, X, c.plan)
+    assert torch.equal(Y, ops.spmm(c.rowptr, c.col, X, c.plan))             # run-to-run deterministic
+    lhs = (Z.double() * Y.double()).sum()
+    rhs = (ops.spmm(t.rowptr, t.col, Z, t.plan).double() * X.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-7 * abs(float(lhs)) + 1.0
+    # oracle on sampled rows, including the heaviest hub and some empty rows
+    rng = np.random.default_rng(0)
+    rows = np.unique(np.concatenate([rng.integers(0, n, 3000), [int(deg.argmax())], np.flatnonzero((deg == 0).cpu().numpy())[:5]]))
+    rp = rowptr.cpu().numpy()
+    sub_ptr = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(rp[rows + 1] - rp[rows], out=sub_ptr[1:])
+    colc = col.cpu().numpy()
+    sub_col = np.concatenate([colc[rp[r]:rp[r + 1]] for r in rows]) if rows.size else np.zeros(0, np.int32)
+    from oracle import c_spmm
+    ref = torch.from_numpy(c_spmm.spmm_f64acc(sub_ptr, sub_col, X.cpu().numpy()))
+    assert rel_err(Y[torch.from_numpy(rows).to(cuda)], ref) < TOL
