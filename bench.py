@@ -261,7 +261,7 @@ def pubmed_leg(dev, steps=100, warmup=5):
     g, X = synthetic.planetoid_like("pubmed", seed=0)
     torch.manual_seed(0)
     model = G.GAE(500, [32, 16]).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True, fused=True)
     g.to(dev)
     Xd = X.to(dev)
     pw = G.pos_weight_of(g, transductive=True)

@@ -35,6 +35,21 @@ class HubPlanStruct(Structure):
     ]
 
 
+MAX_LAYERS = 8
+
+
+class StepDesc(Structure):
+    """Mirror of gae_step_desc_t."""
+    _fields_ = [
+        ("n_layers", c_int32),
+        ("dims", c_int32 * (MAX_LAYERS + 1)),
+        ("acts", c_int32 * MAX_LAYERS),
+        ("dropout_p", c_float),
+        ("pos_weight", c_float),
+        ("per_graph", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gae_b200.h declares
 SIGNATURES = {
     "gae_version": (c_char_p, []),
@@ -70,6 +85,12 @@ SIGNATURES = {
                                               c_void_p, c_void_p, c_double, c_float, c_int32, c_void_p, c_void_p,
                                               c_int64, c_void_p, c_int64, c_void_p]),
     "gae_decoder_logits_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
+    "gae_step_ws_bytes": (c_int64, [POINTER(StepDesc), c_int64, POINTER(HubPlanStruct), POINTER(HubPlanStruct)]),
+    "gae_step_fwd_bwd_f32": (c_int, [POINTER(StepDesc), c_int64, c_void_p, c_void_p, POINTER(HubPlanStruct), c_void_p,
+                                     c_void_p, POINTER(HubPlanStruct), c_void_p, c_int64, POINTER(c_void_p),
+                                     POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int32,
+                                     c_void_p, c_void_p, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_void_p,
+                                     c_int64, c_void_p]),
     "gae_in_degrees_i64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gae_batch_offset_cols_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "gae_batch_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,

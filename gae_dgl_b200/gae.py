@@ -151,13 +151,38 @@ class GAE(nn.Module):
         return h
 
     def loss(self, g, pos_weight: Optional[float] = None, mask: Optional[torch.Tensor] = None,
-             transductive: bool = False, per_graph: bool = False):
+             transductive: bool = False, per_graph: bool = False, fused_step: Optional[bool] = None):
         """Fused equivalent of `BCELoss(model.forward(g), adj, pos_weight)`
-        (train_inductive.py:44-48), including the gae.py:53 write-back."""
-        h = self.encode(g)
-        g.ndata['h'] = h
+        (train_inductive.py:44-48), including the gae.py:53 write-back.
+
+        fused_step (default: automatic) runs the whole step -- encoder, decoder loss and the
+        backward -- behind ONE native call (ops.FusedStepFunction); it applies when every layer
+        activation is ReLU / identity and the input features need no gradient.  The layer-by-layer
+        path (what `forward` / `encode` use) computes the same numbers."""
         if pos_weight is None:
             pos_weight = pos_weight_of(g, transductive, per_graph)
+        x = g.ndata['h']
+        codes = [_act_code(conv.apply_mod.activation) for conv in self.layers]
+        can_fuse = all(c is not None for c in codes) and not x.requires_grad and \
+            self.layers[-1].apply_mod.linear.out_features <= 64 and len(self.layers) <= 8
+        if fused_step is None:
+            fused_step = can_fuse
+        if fused_step:
+            if not can_fuse:
+                raise ops.GaeError("fused_step=True needs ReLU/identity activations, leaf features and d_last <= 64")
+            if x.device != g.device:
+                g.to(x.device)
+            dims = [self.layers[0].apply_mod.linear.in_features] + [c.apply_mod.linear.out_features for c in self.layers]
+            params = []
+            for conv in self.layers:
+                params += [conv.apply_mod.linear.weight, conv.apply_mod.linear.bias]
+            st = None if mask is not None else self.decoder._rng_state(x.device)
+            loss, z = ops.FusedStepFunction.apply(x, g, dims, codes, float(pos_weight), float(self.decoder.dropout), mask,
+                                                  st, per_graph, *params)
+            g.ndata['h'] = z
+            return loss
+        h = self.encode(g)
+        g.ndata['h'] = h
         return self.decoder.loss(h, g, pos_weight, mask, per_graph)
 
     reconstruction_loss = loss

@@ -411,3 +411,68 @@ class DecoderLogitsFunction(torch.autograd.Function):
         Zd, m = ctx.saved_tensors
         dZd = (G + G.t()) @ Zd
         return dropout_bwd(dZd, m, ctx.p), None, None, None
+
+
+class FusedStepFunction(torch.autograd.Function):
+    """Whole GAE step behind one C call (gae_step_fwd_bwd_f32): encoder forward, dropout, fused
+    decoder loss and -- when any parameter needs a gradient -- the complete backward, computed
+    eagerly for grad_output = 1 and scaled by the incoming gradient in backward().
+    Returns (loss, embeddings); the embeddings are not differentiable through this path."""
+
+    @staticmethod
+    def forward(ctx, X, graph, dims, acts, pos_weight, p, mask, rng_state, per_graph, *params):
+        from ._lib import StepDesc
+        lib = _lib.load()
+        X = as_rows(X, "features")
+        n = X.shape[0]
+        L = len(dims) - 1
+        csr, csr_t = graph.csr(), graph.csr_t()
+        desc = StepDesc()
+        desc.n_layers = L
+        for i, v in enumerate(dims):
+            desc.dims[i] = int(v)
+        for i, a in enumerate(acts):
+            desc.acts[i] = int(a)
+        desc.dropout_p, desc.pos_weight, desc.per_graph = float(p), float(pos_weight), int(bool(per_graph))
+        Ws = [params[2 * l].contiguous() for l in range(L)]
+        bs = [params[2 * l + 1].contiguous() for l in range(L)]
+        want_grad = any(t.requires_grad for t in params)
+        dev = X.device
+        plan = ctypes.byref(csr.plan.struct) if csr.plan is not None and (csr.plan.n_seg or csr.plan.bins) else None
+        plan_t = ctypes.byref(csr_t.plan.struct) if csr_t.plan is not None and (csr_t.plan.n_seg or csr_t.plan.bins) else None
+        ws_bytes = lib.gae_step_ws_bytes(ctypes.byref(desc), n, plan, plan_t)
+        if ws_bytes <= 0:
+            raise GaeError("gae_step_ws_bytes rejected the configuration")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        Z = alloc_rows(n, dims[-1], dev)
+        dW = [torch.empty_like(w) for w in Ws] if want_grad else []
+        db = [torch.empty_like(b) for b in bs] if want_grad else []
+        arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts]) if ts else None  # noqa: E731
+        lo = hi = None
+        n_pairs = 0.0
+        if per_graph:
+            lo, hi, n_pairs = graph.block_ranges()
+        m = None
+        if mask is not None:
+            m = mask.to(device=dev, dtype=torch.uint8).contiguous()
+            if m.shape != (n, dims[-1]):
+                raise GaeError("dropout mask shape mismatch")
+        elif rng_state is None:
+            raise GaeError("fused step needs a mask or a device RNG state")
+        rc = lib.gae_step_fwd_bwd_f32(ctypes.byref(desc), n, _ptr(csr.rowptr), _ptr(csr.col), plan, _ptr(csr_t.rowptr),
+                                      _ptr(csr_t.col), plan_t, _ptr(X), _ld(X), arr(Ws), arr(bs), _ptr(m),
+                                      _ptr(rng_state), _ptr(lo), _ptr(hi), float(n_pairs), int(want_grad), _ptr(loss),
+                                      _ptr(Z), _ld(Z), arr(dW), arr(db), _ptr(ws), ws_bytes, _stream())
+        _lib.check(rc, "gae_step_fwd_bwd_f32")
+        ctx.grads = [g for pair in zip(dW, db) for g in pair] if want_grad else None
+        ctx.mark_non_differentiable(Z)
+        return loss, Z
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_z):
+        if ctx.grads is None:
+            return (None,) * 9
+        grads = ctx.grads
+        torch._foreach_mul_(grads, g_loss)
+        return (None,) * 9 + tuple(grads)

@@ -60,7 +60,7 @@ class Trainer:
     def __init__(self, model, args, device=None):
         self.model = model
         self.device = device if device is not None else next(model.parameters()).device
-        self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr)
+        self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr, fused=self.device.type == 'cuda')
         self.dense = bool(getattr(args, 'dense_decoder', False))
         self.per_graph = bool(getattr(args, 'per_graph_decoder', False))
         print('Total Parameters:', sum([p.nelement() for p in self.model.parameters()]))
@@ -73,13 +73,16 @@ class Trainer:
         adj_logits = self.model.forward(g)                  # :47
         return BCELoss(adj_logits, adj, pos_weight=pos_weight)     # :48
 
-    def iteration(self, g, train=True):
+    def iteration(self, g, train=True, sync=True):
+        """One step (train_inductive.py:43-53).  sync=True returns loss.item() like the reference
+        (a device->host sync per step); sync=False returns the 0-dim device tensor so the caller can
+        keep the GPU queue full and read the losses once per epoch."""
         loss = self.loss(g)
         if train:
-            self.optim.zero_grad()
+            self.optim.zero_grad(set_to_none=True)
             loss.backward()
             self.optim.step()
-        return loss.item()
+        return loss.item() if sync else loss.detach()
 
     def save(self, epoch, save_dir):
         output_path = os.path.join(save_dir, 'ep{:02}.pkl'.format(epoch))
@@ -169,23 +172,23 @@ def main(argv=None):
     train_losses, val_losses = [], []
     print('Training Start')
     for epoch in range(start_epoch, args.n_epochs):
-        train_loss = 0
         model.train()
+        step_losses = []
         for bg in train_loader:
             bg.set_e_initializer(dgl.init.zero_initializer)
             bg.set_n_initializer(dgl.init.zero_initializer)
-            train_loss += trainer.iteration(bg)
-        train_loss /= len(train_loader)
+            step_losses.append(trainer.iteration(bg, sync=False))      # no host sync inside the epoch
+        train_loss = float(torch.stack(step_losses).sum()) / len(train_loader)
         train_losses.append(train_loss)
         trainer.save(epoch, args.save_dir)
 
-        val_loss = 0
         model.eval()
+        step_losses = []
         for bg in val_loader:
             bg.set_e_initializer(dgl.init.zero_initializer)
             bg.set_n_initializer(dgl.init.zero_initializer)
-            val_loss += trainer.iteration(bg, train=False)
-        val_loss /= len(val_loader)
+            step_losses.append(trainer.iteration(bg, train=False, sync=False))
+        val_loss = float(torch.stack(step_losses).sum()) / len(val_loader)
         val_losses.append(val_loss)
         print('Epoch: {:02d} | Train Loss: {:.4f} | Validation Loss: {:.4f}'.format(epoch, train_loss, val_loss))
     plot(train_losses, val_losses, args.save_dir)

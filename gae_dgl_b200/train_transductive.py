@@ -60,7 +60,7 @@ def train(args, features, g, device, verbose=True):
     model = (VGAE if args.variational else GAE)(in_feats, args.hidden_dims)   # :41
     model.to(device)
     model.train()
-    optim = torch.optim.Adam(model.parameters(), lr=args.lr, capturable=True)   # :43 (capturable: CUDA-graph replay)
+    optim = torch.optim.Adam(model.parameters(), lr=args.lr, capturable=True, fused=True)   # :43 (capturable: CUDA-graph replay)
     g.to(device)
     features = features.to(device)
 

@@ -173,6 +173,36 @@ int gae_decoder_bce_blockdiag_f32(const float *Zd, int64_t ldz, int64_t n, int32
 int gae_decoder_logits_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, float *X,
                            int64_t ldx, void *stream);
 
+/* ---- whole train step behind one call --------------------------------------------------------- */
+/* Encoder forward (gae.py:49-52), dropout + fused decoder loss (gae.py:69-72, train_inductive.py:
+ * 44-48) and, with want_grad, the full backward (train_inductive.py:51) sequenced on `stream` out of
+ * ONE caller-owned workspace: the host cost of a step is a single call (matters on molecule batches
+ * where a step is ~25 kernels of a few microseconds).  The optimiser step stays with the caller.
+ *   W, b, dW, db : HOST arrays [n_layers] of DEVICE pointers (W_l is [dims[l+1], dims[l]] row-major)
+ *   mask_in      : optional injected keep-mask [n, dims[L]] u8; else rng_state (device u64[2]) is used
+ *   blk_lo/hi    : per-node block ranges when desc->per_graph != 0
+ *   Z_out        : embeddings [n, ldz] (written; also what gae.py:53 stores back into ndata['h'])
+ *   dW, db are the gradients of the MEAN loss (grad_output = 1). */
+#define GAE_MAX_LAYERS 8
+typedef struct gae_step_desc_t {
+    int32_t n_layers;
+    int32_t dims[GAE_MAX_LAYERS + 1];   /* in_dim, hidden_dims...                       */
+    int32_t acts[GAE_MAX_LAYERS];       /* GAE_ACT_* per layer (gae.py:36-45)            */
+    float dropout_p;                    /* decoder dropout, gae.py:64                    */
+    float pos_weight;                   /* train_inductive.py:46                         */
+    int32_t per_graph;                  /* 0 = full N x N pairs (reference), 1 = block-diagonal */
+} gae_step_desc_t;
+int64_t gae_step_ws_bytes(const gae_step_desc_t *desc, int64_t n, const gae_hub_plan_t *plan,
+                          const gae_hub_plan_t *plan_t);
+int gae_step_fwd_bwd_f32(const gae_step_desc_t *desc, int64_t n, const int64_t *rowptr,
+                         const int32_t *col, const gae_hub_plan_t *plan, const int64_t *rowptr_t,
+                         const int32_t *col_t, const gae_hub_plan_t *plan_t, const float *X,
+                         int64_t ldx, const float *const *W, const float *const *b,
+                         const uint8_t *mask_in, uint64_t *rng_state, const int64_t *blk_lo,
+                         const int64_t *blk_hi, double n_pairs, int32_t want_grad, float *loss,
+                         float *Z_out, int64_t ldz, float *const *dW, float *const *db, void *ws,
+                         int64_t ws_bytes, void *stream);
+
 /* ---- graph indexing on device ("bit-exact adjacency/degree indexing") ---------------------- */
 /* in_degrees (train_transductive.py:55): deg[v] = rowptr[v+1]-rowptr[v] as int64. */
 int gae_in_degrees_i64(const int64_t *rowptr, int64_t n_rows, int64_t *deg, void *stream);

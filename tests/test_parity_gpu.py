@@ -278,14 +278,17 @@ def _check_step(cuda, g, X, weights, mask, transductive=False):
     model.to(cuda)
     g.to(cuda)
     g.ndata["h"] = X.to(cuda)
-    loss = model.loss(g, mask=mask.to(cuda), transductive=transductive)
-    loss.backward()
-    assert abs(float(loss) - float(loss_ref)) < TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
-    assert rel_err(g.ndata["h"], z_ref) < TOL                       # gae.py:53 write-back = embeddings
-    for layer, (gW, gb) in zip(model.layers, grads_ref):
-        lin = layer.apply_mod.linear
-        assert float((lin.weight.grad.double().cpu() - gW).abs().max()) < TOL * max(float(gW.abs().max()), 1e-30) * 5
-        assert float((lin.bias.grad.double().cpu() - gb).abs().max()) < TOL * max(float(gb.abs().max()), 1e-30) * 5
+    for fused in (True, False):          # one native call per step vs layer-by-layer autograd
+        model.zero_grad(set_to_none=True)
+        g.ndata["h"] = X.to(cuda)
+        loss = model.loss(g, mask=mask.to(cuda), transductive=transductive, fused_step=fused)
+        (2.0 * loss).backward()          # non-unit grad_output exercises the scaling in backward()
+        assert abs(float(loss) - float(loss_ref)) < TOL * abs(float(loss_ref)), (float(loss), float(loss_ref), fused)
+        assert rel_err(g.ndata["h"], z_ref) < TOL                   # gae.py:53 write-back = embeddings
+        for layer, (gW, gb) in zip(model.layers, grads_ref):
+            lin = layer.apply_mod.linear
+            assert float((lin.weight.grad.double().cpu() / 2 - gW).abs().max()) < TOL * max(float(gW.abs().max()), 1e-30) * 5
+            assert float((lin.bias.grad.double().cpu() / 2 - gb).abs().max()) < TOL * max(float(gb.abs().max()), 1e-30) * 5
     return float(loss), model
 
 

@@ -20,7 +20,7 @@ def main():
     packed = PackedGraphDataset(ds, dev)
     torch.manual_seed(0)
     model = G.GAE(39, [32, 16]).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
     rng = np.random.default_rng(0)
     batches = [rng.permutation(4096)[:256] for _ in range(30)]
 

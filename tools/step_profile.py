@@ -18,7 +18,7 @@ def run(name, g, X, in_dim, lr, steps, transductive, graphed=True):
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     model = G.GAE(in_dim, [32, 16]).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True)
     g.to(dev)
     Xd = X.to(dev)
     pw = G.pos_weight_of(g, transductive=transductive)
@@ -48,7 +48,7 @@ def run(name, g, X, in_dim, lr, steps, transductive, graphed=True):
           f"{wall:.3f} ms/step (wall)", flush=True)
     if graphed:
         from gae_dgl_b200.graphed import GraphedTrainStep
-        opt2 = torch.optim.Adam(model.parameters(), lr=lr, capturable=True)
+        opt2 = torch.optim.Adam(model.parameters(), lr=lr, capturable=True, fused=True)
 
         def loss_fn():
             g.ndata["h"] = Xd
