@@ -8,8 +8,8 @@ Graph500 R-MAT (a,b,c,d = .57,.19,.19,.05), scale 22+log2(N), |E| = 1e8 * N dire
 no dedup, vertex labels scrambled (Graph500), d = 64 fp32 features.  One "step" is the
 encoder aggregation train step on that graph: SpMM forward Y = A X followed by SpMM backward
 dX = A^T dY (the N^2 decoder is infeasible at |V| >= 4M and is not run).
-metric = |E| / step time.  The Pubmed train step (configs[1]) is reported in the same line
-under "pubmed".
+metric = |E| / step time.  The Pubmed (configs[1]) and ZINC batch=256 (configs[2]) train steps
+are reported in the same line under "pubmed" / "zinc".
 
 --impl reference times the CPU oracle (the reference's DGL path cannot be installed here:
 no dgl wheel, no network) with all host threads on a bounded sample of the same workload.
@@ -234,6 +234,7 @@ def run_reference(args):
     }
     if not args.no_pubmed and n_gpus == 1:
         line["pubmed"] = cpu_pubmed_leg()
+        line["zinc"] = cpu_zinc_leg()
     print(json.dumps(line), flush=True)
 
 
@@ -295,6 +296,74 @@ def pubmed_leg(dev, steps=100, warmup=5):
             "value": e / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "final_loss": last,
             "e2e": {"value": e / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(X.numel() * 4), "d2h_bytes_per_step": 4}}
+
+
+def zinc_leg(dev, steps=60, warmup=5, batch_size=256):
+    """configs[2]: ZINC-shaped inductive step, batch = 256 molecules, hidden 32/16: device collation
+    from the packed dataset + fused native step + Adam, a new random batch every step."""
+    import gae_dgl_b200 as G
+    from gae_dgl_b200 import synthetic
+    from gae_dgl_b200.graph import PackedGraphDataset
+    ds = synthetic.zinc_like_dataset(4096, seed=0)
+    packed = PackedGraphDataset(ds, dev)
+    torch.manual_seed(0)
+    model = G.GAE(39, [32, 16]).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    rng = np.random.default_rng(0)
+    batches = [rng.permutation(len(ds))[:batch_size] for _ in range(steps + warmup)]
+    edges = float(np.mean([packed.edges[b].sum() for b in batches[warmup:]]))
+
+    def step(ids):
+        loss = model.loss(packed.batch(ids))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for ids in batches[:warmup]:
+        step(ids)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for ids in batches[warmup:]:
+        last = step(ids)
+    last = float(last)                       # one sync at the end; includes host collation cost
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    return {"workload": f"zinc_like batch={batch_size} (mean {edges:.0f} directed edges/batch) inductive train step: "
+                        "device collation + fwd + bwd + Adam, wall clock incl. host overhead",
+            "value": edges / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "final_loss": last}
+
+
+def cpu_zinc_leg(steps=2, batch_size=256):
+    """Reference inductive step on the host (train_inductive.py:43-53): dgl.batch, dense adj, forward, BCE,
+    backward, Adam."""
+    from gae_dgl_b200 import synthetic
+    from oracle import gae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ds = synthetic.zinc_like_dataset(batch_size * (steps + 1), seed=0)
+    torch.manual_seed(0)
+    model = O.OracleGAE(39, [32, 16])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ts, edges = [], []
+    for k in range(steps + 1):
+        part = ds[k * batch_size:(k + 1) * batch_size]
+        t0 = time.perf_counter()
+        s, d, n = O.batch_graphs([(*g.edges(), g.number_of_nodes()) for g in part])
+        rowptr, col = O.coo_to_csr(s, d, n)
+        X = torch.cat([g.ndata["h"] for g in part])
+        adj = O.dense_adj(s, d, n)
+        pw = O.pos_weight_inductive(adj)
+        loss = O.bce_loss(model(rowptr, col, X), adj, pw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss)
+        if k:
+            ts.append(time.perf_counter() - t0)
+            edges.append(s.numel())
+    t = min(ts)
+    return {"value": float(np.mean(edges)) / t, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"batch={batch_size} ZINC-shaped train step incl. collation, best of {steps}", "ms_per_step": t * 1e3}
 
 
 def run_ours(args):
@@ -439,6 +508,8 @@ def run_ours(args):
         if not args.no_pubmed:
             line["pubmed"] = pubmed_leg(dev)
             line["pubmed"]["cpu_baseline"] = cpu_pubmed_leg()
+            line["zinc"] = zinc_leg(dev)
+            line["zinc"]["cpu_baseline"] = cpu_zinc_leg()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -44,9 +44,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-        // stage A tile [BM x BK]
-        for (int i = tid; i < BM * BK; i += GEMM_THREADS) {
+    // register double buffering: the global loads of tile t+1 are issued before the FMAs of tile t
+    constexpr int NA = BM * BK / GEMM_THREADS, NB = BN * BK / GEMM_THREADS;
+    float ra[NA], rb[NB];
+    auto fetch = [&](int64_t k0) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int i = tid + q * GEMM_THREADS;
             int mm, kk;
             if (A_KC) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
             const int64_t m = m0 + mm, k = k0 + kk;
@@ -55,15 +59,38 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmArgs g) {
                 v = __ldg(g.A + m * g.a_rs + k * g.a_cs);
                 if (g.Mask && !(__ldg(g.Mask + m * g.m_rs + k * g.m_cs) > 0.f)) v = 0.f;
             }
-            As[kk][mm] = v;
+            ra[q] = v;
         }
-        for (int i = tid; i < BN * BK; i += GEMM_THREADS) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int i = tid + q * GEMM_THREADS;
             int nn, kk;
             if (B_KC) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
             const int64_t n = n0 + nn, k = k0 + kk;
-            Bs[kk][nn] = (n < g.N && k < kend) ? __ldg(g.B + k * g.b_rs + n * g.b_cs) : 0.f;
+            rb[q] = (n < g.N && k < kend) ? __ldg(g.B + k * g.b_rs + n * g.b_cs) : 0.f;
         }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int i = tid + q * GEMM_THREADS;
+            int mm, kk;
+            if (A_KC) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
+            As[kk][mm] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int i = tid + q * GEMM_THREADS;
+            int nn, kk;
+            if (B_KC) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
+            Bs[kk][nn] = rb[q];
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        stash();
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];

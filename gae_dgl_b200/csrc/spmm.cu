@@ -110,10 +110,11 @@ __global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
     if (CACHE == 1) pol = make_policy_evict_last();
 
     const int d = a.d;
-    // LPR == 32: loop over 128-float column chunks (wide features, e.g. d_in = 500 / 1433).
-    // Every lane runs the same trip count so the shuffles below stay warp-convergent.
-    const int nchunk = (LPR == 32) ? ((d + 127) >> 7) : 1;
-    for (int ch = 0; ch < nchunk; ++ch) {
+    // LPR == 32: 128-float column chunks (wide features, e.g. d_in = 500 / 1433).
+    // (wide rows: the 128-float column chunks are independent, so they are spread over gridDim.y
+    // instead of being walked one after the other by the same warp)
+    {
+        const int ch = (LPR == 32) ? (int)blockIdx.y : 0;
         const int c4 = sub + ch * LPR;
         const bool colok = c4 * 4 < d;
         const float *xb = a.X + (int64_t)(colok ? c4 : 0) * 4;  // idle lanes re-read column 0
@@ -266,7 +267,8 @@ static cudaError_t launch_one(const SpmmArgs &a, int block, cudaStream_t st) {
     const int64_t warps = cdiv(a.n_items, RPW);
     const int64_t blocks = cdiv(warps, wpb);
     if (blocks == 0) return cudaSuccess;
-    spmm_vec_kernel<LPR, GPR, U, VALS, CACHE, SEG, MINB><<<(unsigned)blocks, block, 0, st>>>(a);
+    const dim3 grid((unsigned)blocks, LPR == 32 ? (unsigned)((a.d + 127) >> 7) : 1u);
+    spmm_vec_kernel<LPR, GPR, U, VALS, CACHE, SEG, MINB><<<grid, block, 0, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }

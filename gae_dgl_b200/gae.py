@@ -177,8 +177,9 @@ class GAE(nn.Module):
             for conv in self.layers:
                 params += [conv.apply_mod.linear.weight, conv.apply_mod.linear.bias]
             st = None if mask is not None else self.decoder._rng_state(x.device)
+            need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in params)
             loss, z = ops.FusedStepFunction.apply(x, g, dims, codes, float(pos_weight), float(self.decoder.dropout), mask,
-                                                  st, per_graph, *params)
+                                                  st, per_graph, need_grad, *params)
             g.ndata['h'] = z
             return loss
         h = self.encode(g)

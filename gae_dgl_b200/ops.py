@@ -420,7 +420,7 @@ class FusedStepFunction(torch.autograd.Function):
     Returns (loss, embeddings); the embeddings are not differentiable through this path."""
 
     @staticmethod
-    def forward(ctx, X, graph, dims, acts, pos_weight, p, mask, rng_state, per_graph, *params):
+    def forward(ctx, X, graph, dims, acts, pos_weight, p, mask, rng_state, per_graph, need_grad, *params):
         from ._lib import StepDesc
         lib = _lib.load()
         X = as_rows(X, "features")
@@ -436,7 +436,7 @@ class FusedStepFunction(torch.autograd.Function):
         desc.dropout_p, desc.pos_weight, desc.per_graph = float(p), float(pos_weight), int(bool(per_graph))
         Ws = [params[2 * l].contiguous() for l in range(L)]
         bs = [params[2 * l + 1].contiguous() for l in range(L)]
-        want_grad = any(t.requires_grad for t in params)
+        want_grad = bool(need_grad)
         dev = X.device
         plan = ctypes.byref(csr.plan.struct) if csr.plan is not None and (csr.plan.n_seg or csr.plan.bins) else None
         plan_t = ctypes.byref(csr_t.plan.struct) if csr_t.plan is not None and (csr_t.plan.n_seg or csr_t.plan.bins) else None
@@ -472,7 +472,7 @@ class FusedStepFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_z):
         if ctx.grads is None:
-            return (None,) * 9
+            return (None,) * 10
         grads = ctx.grads
         torch._foreach_mul_(grads, g_loss)
-        return (None,) * 9 + tuple(grads)
+        return (None,) * 10 + tuple(grads)

@@ -77,7 +77,8 @@ class Trainer:
         """One step (train_inductive.py:43-53).  sync=True returns loss.item() like the reference
         (a device->host sync per step); sync=False returns the 0-dim device tensor so the caller can
         keep the GPU queue full and read the losses once per epoch."""
-        loss = self.loss(g)
+        with torch.set_grad_enabled(train):      # validation needs no gradient work
+            loss = self.loss(g)
         if train:
             self.optim.zero_grad(set_to_none=True)
             loss.backward()

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q -k "not full_size" > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+python tools/step_profile.py --steps 50 --which zinc,cora > gpurun_out/sp_fused.log 2>&1
+python tools/collate_bench.py > gpurun_out/collate_bench2.log 2>&1
+tail -n 12 gpurun_out/pytest_gpu.log; grep "ms/step" gpurun_out/sp_fused.log; grep "ms/batch" gpurun_out/collate_bench2.log
