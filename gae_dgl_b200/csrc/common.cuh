@@ -14,9 +14,9 @@ int32_t tuning(int idx);
 
 enum TuningIdx {
     T_SPMM_VARIANT = 0,  // 0 = register gather (LDG.128), 1 = streaming + cp.async.bulk (TMA), 2 = streaming + LDGSTS
-    T_SPMM_UNROLL,       // gathers in flight per lane group (4 / 8 / 16)
-    T_SPMM_BLOCK,        // threads per CTA (128 / 256 / 512)
-    T_SPMM_CACHE,        // 0 = plain ld.global.nc ; 1 = X evict_last + streaming idx/Y
+    T_SPMM_UNROLL,       // gathers in flight per lane (2 / 4 / 8); sets the register budget / occupancy
+    T_SPMM_BLOCK,        // threads per CTA (32 / 64 / 128)
+    T_SPMM_CACHE,        // 0 = plain ld.global.nc ; 1 = X gathers with an L2 evict_last policy + streaming Y stores
     T_SPMM_ROWS_PER_WARP,// 1 = warp per row, 2 = half-warp per row (d <= 64)
     T_DEC_SPLITS,        // 0 = auto
     T_SPMM_STAGES,       // streaming variant: batches of 32 rows in flight per warp (2/3/4)
@@ -90,30 +90,11 @@ __device__ __forceinline__ float4 f4_shfl_xor(const float4 &v, int m) {
     return r;
 }
 
-// 128-bit read-only gather of a feature row slice.
-__device__ __forceinline__ float4 ldg_f4(const float *p) {
-    return __ldg(reinterpret_cast<const float4 *>(p));
-}
-// Same, keeping the line resident in L2 (hub source rows are re-read by many dst rows).
-__device__ __forceinline__ float4 ldg_f4_evict_last(const float *p, uint64_t policy) {
-    float4 r;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p), "l"(policy));
-    return r;
-}
 __device__ __forceinline__ uint64_t make_policy_evict_last() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ uint64_t make_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// Streaming (read-once) index load: do not pollute L1, evict first from L2.
-__device__ __forceinline__ int ld_stream_i32(const int32_t *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream_f4(float *p, const float4 &v) {
     __stcs(reinterpret_cast<float4 *>(p), v);
 }

@@ -51,10 +51,6 @@ __device__ __forceinline__ float4 gather_f4(const float *p, uint64_t pol) {
         asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                      : "l"(p), "l"(pol));
-    } else if (CACHE == 2) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                     : "l"(p));
     } else {
         asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)

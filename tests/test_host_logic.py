@@ -207,3 +207,37 @@ def test_pos_weight_matches_reference_expression():
     adj = g.adjacency_matrix().to_dense()
     assert G.pos_weight_of(g) == float(O.pos_weight_inductive(adj))
     assert G.pos_weight_of(g, transductive=True) == float(O.pos_weight_transductive(adj)[0])
+
+
+def test_link_prediction_eval_utility():
+    from gae_dgl_b200 import evaluate
+    g, _ = synthetic.planetoid_like("cora", seed=0)
+    src, dst = g.edges()
+    ni, nj = evaluate.sample_non_edges(g, 500, seed=1)
+    present = set((src * 2708 + dst).tolist())
+    assert all((int(a) * 2708 + int(b)) not in present and a != b for a, b in zip(ni, nj))
+    # embeddings that encode the graph separate edges from non-edges; random ones do not
+    torch.manual_seed(0)
+    z_rand = torch.randn(2708, 16)
+    auc_r, ap_r = evaluate.link_prediction_metrics(z_rand, (src[:500], dst[:500]), (ni, nj))
+    assert 0.4 < auc_r < 0.6
+    adj = g.adjacency_matrix().to_dense()
+    u, s_, _ = torch.linalg.svd(adj + torch.eye(2708))
+    z_good = u[:, :64] * s_[:64].sqrt()
+    auc_g, ap_g = evaluate.link_prediction_metrics(z_good, (src[:500], dst[:500]), (ni, nj))
+    assert auc_g > 0.9 and ap_g > 0.9
+
+
+def test_step_desc_matches_header(lib_built):
+    """ctypes mirrors of the C structs have the sizes the header implies."""
+    assert ctypes.sizeof(_lib.StepDesc) == 4 + 4 * 9 + 4 * 8 + 4 + 4 + 4
+    assert ctypes.sizeof(_lib.HubPlanStruct) == 4 + 4 + 8 + 8 + 8 * 3 + 8 * 3 + 8 * 3
+    lib = _lib.load()
+    d = _lib.StepDesc()
+    d.n_layers = 0
+    assert lib.gae_step_ws_bytes(ctypes.byref(d), 10, None, None) == 0          # rejected, not a crash
+    d.n_layers = 2
+    d.dims[0], d.dims[1], d.dims[2] = 39, 32, 16
+    a = lib.gae_step_ws_bytes(ctypes.byref(d), 1000, None, None)
+    b = lib.gae_step_ws_bytes(ctypes.byref(d), 2000, None, None)
+    assert 0 < a < b

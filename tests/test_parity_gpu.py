@@ -540,3 +540,31 @@ def test_spmm_full_size_c4_properties(cuda):
     from oracle import c_spmm
     ref = torch.from_numpy(c_spmm.spmm_f64acc(sub_ptr, sub_col, X.cpu().numpy()))
     assert rel_err(Y[torch.from_numpy(rows).to(cuda)], ref) < TOL
+
+
+def test_c_abi_error_paths_on_device(cuda):
+    """Error behaviour of the C ABI: codes, messages, no partial work on bad input."""
+    import ctypes
+    lib = _lib.load()
+    Z = torch.randn(64, 80, device=cuda)
+    rp = torch.zeros(65, dtype=torch.int64, device=cuda)
+    cl = torch.zeros(0, dtype=torch.int32, device=cuda)
+    assert lib.gae_decoder_ws_bytes(64, 80) == 0                          # d > 64 unsupported
+    with pytest.raises(G.GaeError):
+        ops.decoder_bce(Z, rp, cl, rp, cl, 1.0, True, True)
+    ws = torch.empty(16, dtype=torch.uint8, device=cuda)
+    loss = torch.zeros((), device=cuda)
+    Z16 = torch.randn(64, 16, device=cuda)
+    rc = lib.gae_decoder_bce_f32(Z16.data_ptr(), 16, 64, 16, rp.data_ptr(), cl.data_ptr(), None, None, 1.0, 1,
+                                 loss.data_ptr(), None, 0, ws.data_ptr(), 16, None)
+    assert rc == -3 and b"workspace" in lib.gae_last_error_string()       # GAE_ERR_WORKSPACE
+    rc = lib.gae_decoder_bce_f32(Z16.data_ptr(), 16, 64, 16, rp.data_ptr(), cl.data_ptr(), None, None, 1.0, 3,
+                                 loss.data_ptr(), None, 0, ws.data_ptr(), 16, None)
+    assert rc == -1                                                       # gradient without dZ / CSR^T
+    assert lib.gae_linear_fwd_f32(Z16.data_ptr(), 8, Z16.data_ptr(), None, Z16.data_ptr(), 16, 64, 16, 16, 0, None) == -1
+    assert lib.gae_dropout_fwd_f32(Z16.data_ptr(), 16, Z16.data_ptr(), 16, ws.data_ptr(), 64, 16, 1.5, 0, 0, 0, None) == -1
+    # an all-isolated-nodes graph trains without NaNs only if the loss is defined: pos_weight = inf is the
+    # reference's behaviour too (division by adj.sum() == 0); the decoder itself stays finite for finite pw
+    l, dz = ops.decoder_bce(Z16, rp, cl, rp, cl, 5.0, True, True)
+    ref = torch.nn.functional.softplus(Z16.double().cpu() @ Z16.double().cpu().t()).mean()
+    assert abs(float(l) - float(ref)) < TOL * float(ref) and bool(torch.isfinite(dz).all())
