@@ -415,6 +415,7 @@ extern "C" int gae_hub_plan_count_host(const int64_t *rowptr, int64_t n_rows, in
                                        int64_t *n_long, int64_t *n_seg) {
     GAE_CHECK_ARG(rowptr && n_long && n_seg, "null pointer");
     GAE_CHECK_ARG(seg_len > 0 && n_rows >= 0, "seg_len must be > 0");
+    GAE_CHECK_ARG(n_rows < ((int64_t)1 << 31), "row ids are int32: n_rows must be < 2^31");
     int64_t nl = 0, ns = 0;
     for (int64_t v = 0; v < n_rows; ++v) {
         const int64_t deg = rowptr[v + 1] - rowptr[v];
@@ -432,8 +433,9 @@ extern "C" int gae_row_bins_host(const int64_t *rowptr, int64_t n_rows, int32_t 
     for (int64_t v = 0; v < n_rows; ++v) {
         const int64_t deg = rowptr[v + 1] - rowptr[v];
         if (deg == 0) { if (empty_rows) empty_rows[ne] = (int32_t)v; ++ne; }
+        else if (deg > seg_len) { /* hub row: owned by the segment pass, in no bin */ }
         else if (deg <= short_max) { if (short_rows) short_rows[ns] = (int32_t)v; ++ns; }
-        else if (deg <= seg_len) { if (mid_rows) mid_rows[nm] = (int32_t)v; ++nm; }
+        else { if (mid_rows) mid_rows[nm] = (int32_t)v; ++nm; }
     }
     counts[0] = ne; counts[1] = ns; counts[2] = nm;
     return GAE_OK;
