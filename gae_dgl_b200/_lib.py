@@ -32,6 +32,7 @@ class HubPlanStruct(Structure):
         ("empty_rows", c_void_p),
         ("short_rows", c_void_p),
         ("mid_rows", c_void_p),
+        ("seg_order", c_void_p),
     ]
 
 

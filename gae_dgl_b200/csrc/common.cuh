@@ -22,6 +22,7 @@ enum TuningIdx {
     T_SPMM_STAGES,       // streaming variant: batches of 32 rows in flight per warp (2/3/4)
     T_SPMM_BINS,         // 1 = use the plan's degree bins when present, 0 = single row pass
     T_DEC_ROWS,          // decoder dense pass: query rows per thread for d <= 16 (1 or 2)
+    T_SPMM_SEG_ORDER,    // 1 = walk hub segments in the plan's seg_order (source-id order), 0 = row-major
     T_COUNT
 };
 

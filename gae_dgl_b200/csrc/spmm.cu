@@ -39,6 +39,8 @@ struct SpmmArgs {
     const int32_t *seg_row;
     // optional indirection: item -> row (degree-binned launches)
     const int32_t *row_list;
+    // optional processing order of the segments
+    const int32_t *seg_order;
 };
 
 // All gathers are `asm volatile` so that their program order (U index loads, then U row
@@ -93,13 +95,14 @@ __global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
             }
             out = a.Y + row * a.ldy;
         } else {
-            const int32_t k = __ldg(a.seg_row + item);
+            const int64_t j = a.seg_order ? (int64_t)__ldg(a.seg_order + item) : item;   // segment id
+            const int32_t k = __ldg(a.seg_row + j);
             const int64_t row = __ldg(a.long_row + k);
-            const int64_t s = item - __ldg(a.long_seg_ptr + k);
+            const int64_t s = j - __ldg(a.long_seg_ptr + k);
             const int64_t r0 = __ldg(a.rowptr + row), r1 = __ldg(a.rowptr + row + 1);
             start = r0 + s * (int64_t)a.seg_len;
             end = min(start + (int64_t)a.seg_len, r1);
-            out = a.Y + item * a.ldy;
+            out = a.Y + j * a.ldy;
         }
     }
     uint64_t pol = 0;
@@ -388,6 +391,8 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
         SpmmArgs s = a;
         s.Y = partial_ws; s.ldy = ldp; s.n_items = plan->n_seg; s.seg_len = plan->seg_len;
         s.long_row = plan->long_row; s.long_seg_ptr = plan->long_seg_ptr; s.seg_row = plan->seg_row;
+        s.row_list = nullptr;
+        s.seg_order = tuning(T_SPMM_SEG_ORDER) ? plan->seg_order : nullptr;
         GAE_CUDA(launch_vec<true>(s, 1, unroll, cache, block, st));
         const int64_t threads = plan->n_long * ((d + 3) / 4);
         spmm_hub_reduce_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(

@@ -112,6 +112,15 @@ def coo_to_csr_torch(src: torch.Tensor, dst: torch.Tensor, n: int, n_cols: Optio
     return rowptr, col
 
 
+def _plan_for(rowptr: torch.Tensor, col: torch.Tensor, seg_len: int) -> Optional[ops.HubPlan]:
+    """Hub-row plan (+ degree bins, + segment order) of a device CSR; None on CPU."""
+    if not rowptr.is_cuda:
+        return None
+    plan = ops.build_hub_plan(rowptr, seg_len)
+    ops.order_segments_by_source(plan, rowptr, col)
+    return plan
+
+
 class DGLGraph:
     """Directed multigraph with node features; edges are (src -> dst)."""
 
@@ -168,11 +177,10 @@ class DGLGraph:
         g._n = rowptr.numel() - 1
         g._device = rowptr.device
         g._frozen_edges = int(col.numel())
-        plan = ops.build_hub_plan(rowptr, seg_len) if rowptr.is_cuda else None
-        g._dev_csr = CSR(rowptr, col, plan)
+        g._dev_csr = CSR(rowptr, col, _plan_for(rowptr, col, seg_len))
         if csr_t is not None:
             rt, ct = csr_t
-            g._dev_csr_t = CSR(rt, ct, ops.build_hub_plan(rt, seg_len) if rt.is_cuda else None)
+            g._dev_csr_t = CSR(rt, ct, _plan_for(rt, ct, seg_len))
         return g
 
     def add_nodes(self, num: int) -> None:
@@ -251,8 +259,7 @@ class DGLGraph:
     def _make_dev(self, host) -> CSR:
         rowptr = torch.from_numpy(host[0]).to(self._device)
         col = torch.from_numpy(host[1]).to(self._device)
-        plan = ops.build_hub_plan(rowptr, self._seg_len) if self._device.type == "cuda" else None
-        return CSR(rowptr, col, plan)
+        return CSR(rowptr, col, _plan_for(rowptr, col, self._seg_len))
 
     def csr(self) -> CSR:
         """In-edge CSR (rows = dst) on the graph's device."""
@@ -268,7 +275,7 @@ class DGLGraph:
                 deg = rp[1:] - rp[:-1]
                 dst = torch.repeat_interleave(torch.arange(self._n, device=rp.device), deg)
                 rt, ct = coo_to_csr_torch(dst, col.to(torch.int64), self._n)
-                self._dev_csr_t = CSR(rt, ct, ops.build_hub_plan(rt, self._seg_len) if rt.is_cuda else None)
+                self._dev_csr_t = CSR(rt, ct, _plan_for(rt, ct, self._seg_len))
             else:
                 self._dev_csr_t = self._make_dev(self.host_csr_t())
         return self._dev_csr_t
@@ -325,8 +332,7 @@ class DGLGraph:
             else:  # adopted CSR: move the tensors
                 c = self._dev_csr
                 self._dev_csr = CSR(c.rowptr.to(device), c.col.to(device), None)
-                if device.type == "cuda":
-                    self._dev_csr.plan = ops.build_hub_plan(self._dev_csr.rowptr, self._seg_len)
+                self._dev_csr.plan = _plan_for(self._dev_csr.rowptr, self._dev_csr.col, self._seg_len)
                 self._dev_csr_t = None
         for frame in (self.ndata, self.edata):
             for k in list(frame.keys()):

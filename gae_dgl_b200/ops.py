@@ -99,11 +99,28 @@ class HubPlan:
     seg_row: torch.Tensor
     struct: HubPlanStruct
     bins: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None   # (empty, short, mid) row lists
+    seg_order: Optional[torch.Tensor] = None                                 # int32 permutation of the segments
 
     def workspace(self, d: int, device) -> Optional[torch.Tensor]:
         if self.n_seg == 0:
             return None
         return torch.empty((self.n_seg, round_up4(d)), dtype=torch.float32, device=device)
+
+
+def order_segments_by_source(plan: "HubPlan", rowptr: torch.Tensor, col: torch.Tensor) -> None:
+    """Fill plan.seg_order: the hub segments sorted by their first source id (stable), so that
+    warps running at the same time gather from the same band of X (L2-resident).  Index-only work
+    done once per graph with device tensor ops."""
+    if plan.n_seg == 0:
+        return
+    dev = rowptr.device
+    seg = torch.arange(plan.n_seg, device=dev, dtype=torch.int64)
+    k = plan.seg_row[:plan.n_seg].to(torch.int64)
+    row = plan.long_row[:plan.n_long].to(torch.int64)[k]
+    first_edge = rowptr[row] + (seg - plan.long_seg_ptr[k]) * plan.seg_len
+    order = torch.argsort(col[first_edge].to(torch.int64), stable=True).to(torch.int32).contiguous()
+    plan.seg_order = order
+    plan.struct.seg_order = order.data_ptr()
 
 
 def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN, bins: Optional[bool] = None) -> HubPlan:

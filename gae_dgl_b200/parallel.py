@@ -93,7 +93,10 @@ def build_halo_plan(src: torch.Tensor, dst: torch.Tensor, n_global: int, rank: i
     req = halo_ids - b[owner_of]                              # owner-local row index
     send_idx = torch.empty(int(sc.sum()), dtype=torch.int64, device=dev)
     all_to_all_v(send_idx, req, send_counts, recv_counts, group)
-    plan = ops.build_hub_plan(rowptr, seg_len) if rowptr.is_cuda else None
+    plan = None
+    if rowptr.is_cuda:
+        plan = ops.build_hub_plan(rowptr, seg_len)
+        ops.order_segments_by_source(plan, rowptr, col32)
     return HaloPlan(rank, world, bounds, n_local, n_halo, halo_ids, recv_counts, send_counts, send_idx, rowptr,
                     col32, plan, int(src.numel()))
 

@@ -84,6 +84,11 @@ typedef struct gae_hub_plan_t {
     const int32_t *empty_rows;   /* [n_empty] rows with in-degree 0                         */
     const int32_t *short_rows;   /* [n_short] rows with in-degree in [1, short_max]          */
     const int32_t *mid_rows;     /* [n_mid]   rows with in-degree in (short_max, seg_len]    */
+    /* Optional processing order of the segments (a permutation of [0, n_seg), NULL = row-major).
+     * Ordering them by their first source id makes concurrently running warps gather from the same
+     * narrow band of X, which then stays resident in L2 (results are unchanged: every segment still
+     * writes its own partial row, reduced in the same fixed order). */
+    const int32_t *seg_order;
 } gae_hub_plan_t;
 
 /* ---- K1 / K2: CSR SpMM, Y = A X (sum aggregation) -------------------------------------- */

@@ -231,7 +231,7 @@ def test_link_prediction_eval_utility():
 def test_step_desc_matches_header(lib_built):
     """ctypes mirrors of the C structs have the sizes the header implies."""
     assert ctypes.sizeof(_lib.StepDesc) == 4 + 4 * 9 + 4 * 8 + 4 + 4 + 4
-    assert ctypes.sizeof(_lib.HubPlanStruct) == 4 + 4 + 8 + 8 + 8 * 3 + 8 * 3 + 8 * 3
+    assert ctypes.sizeof(_lib.HubPlanStruct) == 4 + 4 + 8 + 8 + 8 * 3 + 8 * 3 + 8 * 3 + 8
     lib = _lib.load()
     d = _lib.StepDesc()
     d.n_layers = 0

@@ -55,6 +55,11 @@ def test_spmm_parity(cuda, d, rows_per_warp):
             plan = ops.build_hub_plan(rp, seg_len, bins=bins) if seg_len else None
             if seg_len:
                 assert plan.n_long >= 1
+                if bins:      # source-ordered segment walk: same partials, same ordered reduce -> same bits
+                    base = ops.spmm(rp, cl, X.to(cuda), plan)
+                    ops.order_segments_by_source(plan, rp, cl)
+                    assert sorted(plan.seg_order.tolist()) == list(range(plan.n_seg))
+                    assert torch.equal(ops.spmm(rp, cl, X.to(cuda), plan), base)
             if bins:   # degree-binned row pass: every row lands in exactly one bin
                 ne, ns, nm = (int(plan.struct.n_empty), int(plan.struct.n_short), int(plan.struct.n_mid))
                 assert ne + ns + nm + plan.n_long == n and ne >= 5

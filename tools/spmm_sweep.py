@@ -73,6 +73,7 @@ def main():
     seg_lens = [int(s) for s in args.seg_lens.split(",")]
     if not args.sweep:
         plan = ops.build_hub_plan(rowptr, seg_lens[0])
+        ops.order_segments_by_source(plan, rowptr, col)
         ws = plan.workspace(args.d, dev)
         ms = timeit(plan, ws, args.iters)
         print(f"default tuning: {ms:.3f} ms  {alg / ms / 1e6:.0f} GB/s algorithmic  {args.edges / ms / 1e6:.2f} Gedges/s")
@@ -80,6 +81,7 @@ def main():
     ref = None
     for seg in seg_lens:
         plan = ops.build_hub_plan(rowptr, seg)
+        ops.order_segments_by_source(plan, rowptr, col)
         ws = plan.workspace(args.d, dev)
         for variant in [int(v) for v in args.variants.split(",")]:
             if variant == 0:
@@ -97,9 +99,10 @@ def main():
         _lib.set_tuning("spmm_variant", 0)
         if "0" not in args.variants.split(","):
             continue
-        for block, unroll, cache, rpw, bins in itertools.product(blocks, unrolls, caches, (1, 2),
-                                                                 [int(b) for b in args.bins.split(",")]):
+        for block, unroll, cache, rpw, bins, so in itertools.product(blocks, unrolls, caches, (1,),
+                                                                     [int(b) for b in args.bins.split(",")], (0, 1)):
             _lib.set_tuning("spmm_bins", bins)
+            _lib.set_tuning("spmm_seg_order", so)
             _lib.set_tuning("spmm_block", block)
             _lib.set_tuning("spmm_unroll", unroll)
             _lib.set_tuning("spmm_cache", cache)
@@ -108,7 +111,7 @@ def main():
             if ref is None:
                 ref = Y.clone()
             err = float((Y - ref).abs().max())
-            r = {"seg_len": seg, "block": block, "unroll": unroll, "cache": cache, "rows_per_warp": rpw, "bins": bins, "ms": ms,
+            r = {"seg_len": seg, "block": block, "unroll": unroll, "cache": cache, "rows_per_warp": rpw, "bins": bins, "seg_order": so, "ms": ms,
                  "alg_GBps": alg / ms / 1e6, "maxdiff_vs_first": err}
             results.append(r)
             print(json.dumps(r), flush=True)
