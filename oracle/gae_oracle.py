@@ -17,14 +17,19 @@ What is restated (all citations relative to ``/root/reference``):
   adjacency with summed duplicates, ``pos_weight = (N*N - sum(A)) / sum(A)`` and
   ``binary_cross_entropy_with_logits(logits, A, pos_weight=...)`` (mean over N*N).
 
-PARITY UNPINNED (for the DGL pieces): the reference ships no tests, no golden vectors
-and cannot be imported here (``dgl`` is not installed and there is no network), so the
-message-passing / adjacency / batching semantics are restated from DGL 0.4's documented
-behaviour.  Every *arithmetic* op of the reference other than the
-SpMM (``nn.Linear``, ``F.dropout`` scaling, ``torch.mm``, BCE-with-logits, Adam) is the
-very same torch function the reference calls, executed on CPU, so those pieces are
-pinned by construction.  The known-answer pins of SURVEY.md section 8c are checked in
-``tests/test_oracle_pins.py``.
+PARITY STATUS.  Pinned against the reference's own code for everything the reference
+contains: ``tests/golden/make_golden_reference.py`` imports ``/root/reference/gae_dgl/gae.py``
+unmodified and executes ``class Trainer`` cut out of ``train_inductive.py`` with ``ast``,
+and the committed outputs (``tests/golden/ref_gae_steps.npz``: logits, embeddings, adjacency,
+pos_weight, per-step loss, gradients, weights after Adam, evaluation loss, four model shapes)
+are what ``tests/test_oracle_pins.py`` holds this oracle to.  PARITY UNPINNED for the DGL
+primitives only: ``dgl`` is not installed and not installable here (no wheel, no network;
+the reference ships no tests or golden vectors), so ``update_all(copy_src, sum)``,
+``adjacency_matrix()``, ``dgl.batch`` and ``in_degrees`` run through a small stand-in written
+from DGL 0.4's documented semantics in that generator script (degree-bucketed mailbox sum --
+deliberately not this module's code).  Every other arithmetic op (``nn.Linear``,
+``F.dropout``, ``torch.mm``, BCE-with-logits, Adam) is the very torch function the reference
+calls.  The known-answer pins of SURVEY.md section 8c are checked in the same test file.
 """
 from __future__ import annotations
 

@@ -158,3 +158,73 @@ def test_train_loss_decreases_on_zinc_like_batch():
         opt.zero_grad(); loss.backward(); opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0] and losses[-1] < 1.3
+
+
+# ------------------------------------------------------------------------------------------
+# Pins against outputs of the reference's own code (tests/golden/make_golden_reference.py ran
+# /root/reference/gae_dgl/gae.py and train_inductive.py's Trainer over a DGL stand-in)
+# ------------------------------------------------------------------------------------------
+
+from tests import _ref_fixture as RF  # noqa: E402
+
+
+def _rel(a, ref):
+    a, ref = a.detach().double(), ref.detach().double()
+    return float((a - ref).abs().max() / max(float(ref.abs().max()), 1.0))
+
+
+@pytest.mark.parametrize("tag", RF.CASES)
+def test_oracle_matches_reference_run_indexing(tag):
+    """Bit-exact integer work: dense adjacency (orientation A[dst, src], duplicates summed),
+    in-degrees, dgl.batch offsets and the fp32 pos_weight expression."""
+    c = RF.load_case(tag)
+    s, d, n = O.batch_graphs([(m[0], m[1], m[2]) for m in c.members])
+    assert n == c.n
+    assert torch.equal(O.dense_adj(s, d, n), c.adj)
+    rowptr, col = O.coo_to_csr(s, d, n)
+    assert torch.equal(O.dense_adj_from_csr(rowptr, col), c.adj)
+    assert torch.equal(O.in_degrees(rowptr), c.in_deg)
+    assert float(O.pos_weight_inductive(c.adj)) == c.pos_weight
+
+
+@pytest.mark.parametrize("tag", RF.CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_oracle_matches_reference_run_forward_and_steps(tag, dtype):
+    """gae.py forward / encode and every Trainer.iteration of the reference run: logits,
+    embeddings, loss and gradients per step (each step restarted from the reference's own
+    weights), then the whole Adam trajectory."""
+    c = RF.load_case(tag)
+    s, d, n = O.batch_graphs([(m[0], m[1], m[2]) for m in c.members])
+    rowptr, col = O.coo_to_csr(s, d, n)
+    L = len(c.hidden)
+    w0 = [(W.to(dtype), b.to(dtype)) for W, b in RF.weights_of(c.init, L)]
+    emb = O.encode(rowptr, col, c.X.to(dtype), w0)
+    assert _rel(emb, c.emb) < 1e-5 and _rel(emb, c.encode) < 1e-5
+    assert _rel(O.decoder_logits(emb, c.masks[0], 0.1), c.logits) < 1e-5
+    for step in range(len(c.losses)):
+        start = c.init if step == 0 else c.after[step - 1]
+        loss, _, grads = O.train_step(rowptr, col, c.X, RF.weights_of(start, L), c.masks[step], p=0.1, dtype=dtype)
+        assert abs(float(loss) - c.losses[step]) < 1e-5 * abs(c.losses[step]), (tag, step)
+        for i, (gW, gb) in enumerate(grads):
+            rW = c.grads[step][f"layers.{i}.apply_mod.linear.weight"]
+            rb = c.grads[step][f"layers.{i}.apply_mod.linear.bias"]
+            assert float((gW.double() - rW.double()).abs().max()) < 2e-5 * float(rW.abs().max()), (tag, step, i)
+            assert float((gb.double() - rb.double()).abs().max()) < 2e-5 * max(float(rb.abs().max()), 1e-30), (tag, step, i)
+    # the Adam trajectory (train_inductive.py:40,50-52) and the evaluation call (:100-105)
+    model = O.OracleGAE(c.in_dim, c.hidden)
+    model.load_state_dict(c.init)            # same state_dict keys as the reference module
+    opt = torch.optim.Adam(model.parameters(), lr=c.lr)
+    pw = O.pos_weight_inductive(c.adj)
+    for step in range(len(c.losses)):
+        loss = O.bce_loss(model(rowptr, col, c.X, c.masks[step]), c.adj, pw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - c.losses[step]) < 2e-5 * abs(c.losses[step])
+    sd = model.state_dict()
+    for k, ref in c.after[-1].items():
+        big = c.grads[0][k].abs() > 1e-3 * c.grads[0][k].abs().max()       # Adam's first step is sign(g)
+        assert float((sd[k] - ref)[big].abs().max()) < 1e-5 + 1e-3 * c.lr, (tag, k)
+    with torch.no_grad():
+        ev = O.bce_loss(model(rowptr, col, c.X, c.mask_eval), c.adj, pw)
+    assert abs(float(ev) - c.loss_eval) < 5e-5 * abs(c.loss_eval)

@@ -573,3 +573,76 @@ def test_c_abi_error_paths_on_device(cuda):
     l, dz = ops.decoder_bce(Z16, rp, cl, rp, cl, 5.0, True, True)
     ref = torch.nn.functional.softplus(Z16.double().cpu() @ Z16.double().cpu().t()).mean()
     assert abs(float(l) - float(ref)) < TOL * float(ref) and bool(torch.isfinite(dz).all())
+
+
+# ------------------------------------------------------------------------------------------
+# Replay of the reference's own run (tests/golden/ref_gae_steps.npz: /root/reference/gae_dgl/gae.py
+# and train_inductive.py's Trainer executed over a DGL stand-in, see make_golden_reference.py)
+# ------------------------------------------------------------------------------------------
+
+from tests import _ref_fixture as RF  # noqa: E402
+
+
+def _fixture_graph(c, cuda):
+    """The fixture's graph built through the reference-facing surface (prepare_data.py:48-67 style:
+    DGLGraph() / add_nodes / add_edges / ndata['h'], then dgl.batch as train_inductive.py:34)."""
+    members = []
+    for s, d, n, X in c.members:
+        g = G.DGLGraph()
+        g.add_nodes(n)
+        g.add_edges(s.tolist(), d.tolist())
+        g.ndata["h"] = X.clone()
+        members.append(g)
+    bg = G.batch(members, device=cuda) if len(members) > 1 else members[0].to(cuda)
+    return bg
+
+
+@pytest.mark.parametrize("tag", RF.CASES)
+def test_reference_run_replay(cuda, tag):
+    c = RF.load_case(tag)
+    bg = _fixture_graph(c, cuda)
+    Xd = c.X.to(cuda)
+    # bit-exact indexing against what the reference run saw
+    assert bg.number_of_nodes() == c.n
+    assert torch.equal(bg.adjacency_matrix().to_dense().cpu(), c.adj)
+    assert torch.equal(bg.in_degrees().cpu(), c.in_deg)
+    assert G.pos_weight_of(bg) == c.pos_weight
+    model = G.GAE(c.in_dim, c.hidden)
+    model.load_state_dict(c.init)                       # reference state_dict keys load as they are
+    model.to(cuda)
+    # gae.py:57-61 encode, gae.py:49-55 forward (logits + write-back of the embedding)
+    bg.ndata["h"] = Xd
+    emb = model.encode(bg)
+    assert rel_err(emb, c.encode) < TOL and rel_err(emb, c.emb) < TOL
+    assert rel_err(model.decoder(emb, mask=c.masks[0].to(cuda)), c.logits) < TOL
+    # every Trainer.iteration of the reference run, restarted from the reference's own weights
+    for step in range(len(c.losses)):
+        model.load_state_dict(c.init if step == 0 else c.after[step - 1])
+        for fused in (True, False):
+            model.zero_grad(set_to_none=True)
+            bg.ndata["h"] = Xd
+            loss = model.loss(bg, mask=c.masks[step].to(cuda), fused_step=fused)
+            loss.backward()
+            assert abs(float(loss) - c.losses[step]) < TOL * abs(c.losses[step]), (tag, step, fused)
+            for k, p in model.named_parameters():
+                ref = c.grads[step][k].double()
+                assert float((p.grad.double().cpu() - ref).abs().max()) < 5 * TOL * max(float(ref.abs().max()), 1e-30), \
+                    (tag, step, fused, k)
+    # the Adam trajectory (train_inductive.py:40,50-52) and the evaluation call (:100-105)
+    model.load_state_dict(c.init)
+    opt = torch.optim.Adam(model.parameters(), lr=c.lr)
+    for step in range(len(c.losses)):
+        bg.ndata["h"] = Xd
+        loss = model.loss(bg, mask=c.masks[step].to(cuda))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - c.losses[step]) < 2 * TOL * abs(c.losses[step]), (tag, step)
+    sd = model.state_dict()
+    for k, ref in c.after[-1].items():
+        big = c.grads[0][k].abs() > 1e-3 * c.grads[0][k].abs().max()       # Adam's first step is sign(g)
+        assert float((sd[k].cpu() - ref)[big].abs().max()) < 1e-5 + 1e-3 * c.lr, (tag, k)
+    with torch.no_grad():
+        bg.ndata["h"] = Xd
+        ev = model.loss(bg, mask=c.mask_eval.to(cuda))
+    assert abs(float(ev) - c.loss_eval) < 5 * TOL * abs(c.loss_eval)
