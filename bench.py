@@ -476,6 +476,12 @@ def run_ours(args):
                 "traffic": traffic, "kernel": "spmm_vec_kernel (fwd: rows + hub segments + hub reduce)",
                 "algorithmic_bytes": alg_bytes, "fwd_ms": statistics.mean(fwd_ms), "bwd_ms": statistics.mean(bwd_ms),
                 "peak_source": peak_src}
+    if traffic and world == 1:
+        # the DRAM-side view of the same launch: bytes that actually crossed HBM (ncu capture of this
+        # workload, profiles/spmm_traffic.json) over the live forward time; `frac` above can exceed 1
+        # because gathered source rows are re-read from L2, this one cannot
+        roofline["achieved_dram"] = traffic / (statistics.mean(fwd_ms) * 1e-3) / 1e9
+        roofline["frac_dram"] = roofline["achieved_dram"] / peak
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,

@@ -8,8 +8,9 @@ embedding, gae.py:53), the loss is BCE-with-logits with the transductive pos_wei
 loop-invariant degree norm / adjacency / pos_weight are hoisted (results identical).
 Flags follow :18-26; `--lr`, `--n_epochs`, `--hidden_dims` are honoured here (the reference
 parses and ignores them; its hard-coded values -- lr 1e-2, 500 epochs, [32,16] -- are the
-defaults).  Planetoid data is not on disk: `--dataset` selects a shape-faithful synthetic
-stand-in unless `--data_npz` points at a file with `features`, `src`, `dst` arrays.
+defaults).  `--dataset` reads the Planetoid files `ind.<dataset>.*` from `--data_dir` (data.py, the
+files DGL's load_data would download) when they are there; otherwise it selects a shape-faithful
+synthetic stand-in, or `--data_npz` points at a file with `features`, `src`, `dst` arrays.
 """
 from __future__ import annotations
 
@@ -20,13 +21,14 @@ import numpy as np
 import torch
 from torch.nn.functional import binary_cross_entropy_with_logits as BCELoss
 
+from .data import find_planetoid, load_data as load_planetoid_data, register_data_args
 from .gae import GAE, VGAE, pos_weight_of
 from .graph import DGLGraph
 
 
 def build_parser():
     parser = argparse.ArgumentParser(description='Pre-train GAE')
-    parser.add_argument('--dataset', type=str, default='cora', help='cora | citeseer | pubmed (register_data_args)')
+    register_data_args(parser)                                  # :19  (--dataset, --data_dir)
     parser.add_argument('--n_epochs', '-e', type=int, default=500, help='number of epochs')
     parser.add_argument('--save_dir', '-s', type=str, default='../result', help='result directry')
     parser.add_argument('--in_dim', '-i', type=int, default=39, help='input dimension (ignored: taken from data)')
@@ -49,6 +51,9 @@ def load_data(args):
         z = np.load(args.data_npz)
         g = DGLGraph((z['src'], z['dst'], int(z['features'].shape[0])))
         return torch.from_numpy(z['features'].astype(np.float32)), g
+    if find_planetoid(args.dataset, args.data_dir) is not None:
+        data = load_planetoid_data(args)                        # :37-39
+        return torch.FloatTensor(data.features), DGLGraph(data.graph)      # :38,45
     from .synthetic import planetoid_like
     g, feats = planetoid_like(args.dataset, seed=args.seed or 0)
     print('NOTE: {} is a synthetic stand-in with the dataset\'s shape (no data on disk)'.format(args.dataset))

@@ -241,3 +241,61 @@ def test_step_desc_matches_header(lib_built):
     a = lib.gae_step_ws_bytes(ctypes.byref(d), 1000, None, None)
     b = lib.gae_step_ws_bytes(ctypes.byref(d), 2000, None, None)
     assert 0 < a < b
+
+
+def _write_planetoid(directory, name, n_train, n_all, test_ids, n_feat, n_cls, adj_lists, seed=0):
+    """Writes a tiny dataset in the Planetoid on-disk layout (pickled scipy / ndarray / dict + index file)."""
+    import pickle
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n_test = len(test_ids)
+    feat = lambda k: sp.csr_matrix((rng.random((k, n_feat)) < 0.3).astype(np.float32))  # noqa: E731
+    lab = lambda k: np.eye(n_cls, dtype=np.int32)[rng.integers(0, n_cls, k)]  # noqa: E731
+    parts = {"x": feat(n_train), "y": lab(n_train), "allx": feat(n_all), "ally": lab(n_all),
+             "tx": feat(n_test), "ty": lab(n_test), "graph": adj_lists}
+    for k, v in parts.items():
+        with open(os.path.join(directory, f"ind.{name}.{k}"), "wb") as f:
+            pickle.dump(v, f)
+    with open(os.path.join(directory, f"ind.{name}.test.index"), "w") as f:
+        f.write("\n".join(str(i) for i in test_ids) + "\n")
+    return parts
+
+
+def test_planetoid_loader(tmp_path):
+    """data.load_data reads the files dgl.data.load_data would download (train_transductive.py:37-45):
+    test rows restored to their node ids, Citeseer-style gaps -> zero rows, row-normalised features,
+    undirected simple graph -> both directions in the DGLGraph."""
+    import argparse
+    from gae_dgl_b200 import data as D
+    # 6 labelled/unlabelled nodes (ids 0..5), test ids {8, 6, 9}: id 7 is missing (isolated node)
+    adj = {0: [1, 2], 1: [0], 2: [0, 3, 3], 3: [2], 4: [4], 5: [], 6: [0], 8: [9], 9: [8]}
+    parts = _write_planetoid(str(tmp_path), "citeseer", 3, 6, [8, 6, 9], 7, 3, adj)
+    parser = argparse.ArgumentParser()
+    D.register_data_args(parser)
+    args = parser.parse_args(["--dataset", "citeseer", "--data_dir", str(tmp_path)])
+    data = D.load_data(args)
+    assert data.features.shape == (10, 7) and data.features.dtype == np.float32
+    tx = np.asarray(parts["tx"].todense())
+    raw = np.zeros((10, 7), dtype=np.float32)
+    raw[:6] = np.asarray(parts["allx"].todense())
+    raw[8], raw[6], raw[9] = tx[0], tx[1], tx[2]                  # test.index order
+    sums = raw.sum(1, keepdims=True)
+    expect = np.divide(raw, sums, out=np.zeros_like(raw), where=sums != 0)
+    assert np.allclose(data.features, expect, atol=1e-7)
+    assert float(np.abs(data.features[7]).sum()) == 0.0           # the gap is an all-zero row
+    assert data.labels.shape == (10,) and data.num_labels == 3
+    g = G.DGLGraph(data.graph)                                    # train_transductive.py:45
+    assert g.number_of_nodes() == 10
+    s, d = g.edges()
+    got = sorted(zip(s.tolist(), d.tolist()))
+    und = {(0, 1), (0, 2), (2, 3), (0, 6), (8, 9)}                # duplicates collapsed
+    want = sorted([(a, b) for a, b in und] + [(b, a) for a, b in und] + [(4, 4)])   # self loop once
+    assert got == want
+    assert D.find_planetoid("pubmed", str(tmp_path)) is None
+    with pytest.raises(FileNotFoundError):
+        D.load_data(parser.parse_args(["--dataset", "pubmed", "--data_dir", str(tmp_path)]))
+    # the trainer's loader picks the files up instead of the synthetic stand-in
+    from gae_dgl_b200 import train_transductive as TT
+    a = TT.build_parser().parse_args(["--dataset", "citeseer", "--data_dir", str(tmp_path)])
+    feats, g2 = TT.load_data(a)
+    assert feats.shape == (10, 7) and g2.number_of_edges() == len(want)

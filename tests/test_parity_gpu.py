@@ -71,7 +71,7 @@ def test_spmm_parity(cuda, d, rows_per_warp):
                 assert float(Y[n - 5:].abs().max()) == 0.0          # empty rows are zeros
     finally:
         _lib.set_tuning("spmm_rows_per_warp", 1)
-        _lib.set_tuning("spmm_unroll", 8)
+        _lib.set_tuning("spmm_unroll", 4)
 
 
 @pytest.mark.parametrize("cache", [0, 1, 2])
