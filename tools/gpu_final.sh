@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-end single-GPU validation + refreshed profiles, ordered by priority, every leg under its own timeout:
+#   gpurun --timeout 840 -- 'bash tools/gpu_final.sh'
+# 1. GPU parity tests  2. default bench line  3. ncu launch list of the bench step
+# 4. ncu --set full of the five kernels of one forward SpMM (+ raw CSV page)  5. smoke()
+mkdir -p gpurun_out
+T0=$(date +%s)
+timeout 540 python -m pytest tests -m gpu -q --durations=12 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$? t=$(( $(date +%s) - T0 ))s" >> gpurun_out/pytest_gpu.log
+timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$? t=$(( $(date +%s) - T0 ))s" >> gpurun_out/bench.err
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:spmm_ -c 60 --csv --log-file gpurun_out/launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-pubmed --no-e2e > gpurun_out/ncu_list.log 2>&1; echo "rc=$? t=$(( $(date +%s) - T0 ))s" >> gpurun_out/ncu_list.log
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:spmm_ --launch-skip 10 --launch-count 5 -f -o gpurun_out/spmm_full \
+    python tools/spmm_sweep.py --iters 1 > gpurun_out/ncu_full.log 2>&1; echo "rc=$? t=$(( $(date +%s) - T0 ))s" >> gpurun_out/ncu_full.log
+ncu -i gpurun_out/spmm_full.ncu-rep --page raw --csv > gpurun_out/spmm_full_raw.csv 2>> gpurun_out/ncu_full.log
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$? t=$(( $(date +%s) - T0 ))s" >> gpurun_out/smoke.log
+tail -n 25 gpurun_out/pytest_gpu.log; tail -n 2 gpurun_out/bench.err; cut -c1-1500 gpurun_out/bench.json; tail -n 2 gpurun_out/ncu_list.log gpurun_out/ncu_full.log gpurun_out/smoke.log
