@@ -123,10 +123,15 @@ def order_segments_by_source(plan: "HubPlan", rowptr: torch.Tensor, col: torch.T
     plan.struct.seg_order = order.data_ptr()
 
 
-def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN, bins: Optional[bool] = None) -> HubPlan:
+MID_SORT_DEFAULT = False   # order the mid-row list by descending degree (for the persistent row pass)
+
+
+def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN, bins: Optional[bool] = None,
+                   sort_mid: Optional[bool] = None) -> HubPlan:
     """Split rows with in-degree > seg_len into fixed-length segments (gae_hub_plan_*_host) and,
     for large graphs, bin the remaining rows by degree (gae_row_bins_host).  Runs once per graph
-    on the host copy of rowptr."""
+    on the host copy of rowptr.  sort_mid orders the mid-row list by descending in-degree (stable),
+    which evens out the per-warp work of the persistent row pass; results do not depend on it."""
     lib = _lib.load()
     rp = rowptr.detach().to("cpu", torch.int64).contiguous().numpy()
     n_rows = rp.shape[0] - 1
@@ -157,6 +162,11 @@ def build_hub_plan(rowptr: torch.Tensor, seg_len: int = DEFAULT_SEG_LEN, bins: O
                                          arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data),
                    "gae_row_bins_host")
         ts = tuple(torch.from_numpy(a).to(dev) for a in arrs)
+        n_mid = int(counts[2])
+        if (MID_SORT_DEFAULT if sort_mid is None else sort_mid) and n_mid > 1:
+            mid = ts[2][:n_mid].to(torch.int64)
+            deg = rowptr[mid + 1] - rowptr[mid]
+            ts[2][:n_mid] = mid[torch.argsort(deg, descending=True, stable=True)].to(torch.int32)
         plan.bins = ts
         st.n_empty, st.n_short, st.n_mid = int(counts[0]), int(counts[1]), int(counts[2])
         st.empty_rows, st.short_rows, st.mid_rows = (t.data_ptr() for t in ts)

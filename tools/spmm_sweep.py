@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--bins", type=str, default="1")
     ap.add_argument("--stages", type=str, default="2,3,4")
     ap.add_argument("--out", type=str, default="")
+    ap.add_argument("--persist", type=str, default="0", help="spmm_persist values (bit 0 rows, bit 1 hub segments)")
+    ap.add_argument("--mid-sort", type=str, default="0", help="0 / 1: degree-sorted mid-row list")
+    ap.add_argument("--seg-orders", type=str, default="0,1")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n = 1 << args.scale
@@ -79,8 +82,8 @@ def main():
         print(f"default tuning: {ms:.3f} ms  {alg / ms / 1e6:.0f} GB/s algorithmic  {args.edges / ms / 1e6:.2f} Gedges/s")
         return
     ref = None
-    for seg in seg_lens:
-        plan = ops.build_hub_plan(rowptr, seg)
+    for seg, mid_sort in itertools.product(seg_lens, [int(v) for v in args.mid_sort.split(",")]):
+        plan = ops.build_hub_plan(rowptr, seg, sort_mid=bool(mid_sort))
         ops.order_segments_by_source(plan, rowptr, col)
         ws = plan.workspace(args.d, dev)
         for variant in [int(v) for v in args.variants.split(",")]:
@@ -99,8 +102,10 @@ def main():
         _lib.set_tuning("spmm_variant", 0)
         if "0" not in args.variants.split(","):
             continue
-        for block, unroll, cache, rpw, bins, so in itertools.product(blocks, unrolls, caches, (1,),
-                                                                     [int(b) for b in args.bins.split(",")], (0, 1)):
+        for block, unroll, cache, rpw, bins, so, persist in itertools.product(
+                blocks, unrolls, caches, (1,), [int(b) for b in args.bins.split(",")],
+                [int(v) for v in args.seg_orders.split(",")], [int(v) for v in args.persist.split(",")]):
+            _lib.set_tuning("spmm_persist", persist)
             _lib.set_tuning("spmm_bins", bins)
             _lib.set_tuning("spmm_seg_order", so)
             _lib.set_tuning("spmm_block", block)
@@ -111,7 +116,8 @@ def main():
             if ref is None:
                 ref = Y.clone()
             err = float((Y - ref).abs().max())
-            r = {"seg_len": seg, "block": block, "unroll": unroll, "cache": cache, "rows_per_warp": rpw, "bins": bins, "seg_order": so, "ms": ms,
+            r = {"seg_len": seg, "mid_sort": mid_sort, "persist": persist, "block": block, "unroll": unroll, "cache": cache,
+                 "rows_per_warp": rpw, "bins": bins, "seg_order": so, "ms": ms,
                  "alg_GBps": alg / ms / 1e6, "maxdiff_vs_first": err}
             results.append(r)
             print(json.dumps(r), flush=True)
