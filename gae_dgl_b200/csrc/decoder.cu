@@ -40,10 +40,16 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     else return false;
     c->occ4 = (c_occ4_default() && d <= 16);
     c->mma = d <= 16 ? tuning(T_DEC_MMA) : 0;
-    if (c->mma) c->R = 1;            // the tensor-core kernel covers 128 query rows per CTA
+    if (c->mma < 0 || c->mma > 5) c->mma = 0;
+    int per_sm_mma = 3;
+    int64_t rows_pb = (int64_t)DEC_THREADS * c->R;
+    if (c->mma) {                    // query rows per CTA = 4 warps x 16 MT; resident CTAs per SM by register budget
+        static const int mt[6] = {0, 2, 2, 4, 1, 2}, occ[6] = {0, 3, 3, 2, 5, 4};
+        rows_pb = 64 * mt[c->mma];
+        per_sm_mma = occ[c->mma];
+    }
     c->JT = 2048 / c->D;
-    const int64_t rows_per_block = (int64_t)DEC_THREADS * c->R;
-    c->nb = cdiv(n, rows_per_block);
+    c->nb = cdiv(n, rows_pb);
     int64_t max_splits = cdiv(n, c->JT);
     int64_t want = tuning(T_DEC_SPLITS);
     if (want <= 0) {
@@ -51,7 +57,7 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
         // split count so the last wave is full: wave quantisation cost 20 % at Pubmed size
         // resident CTAs per SM: R = 1 at 64 registers -> 8; R = 2 -> 3 at 143 registers, 4 with OCC4;
         // D = 32 / 64 (one row per thread, ~130 / ~250 registers) -> 3 / 2
-        const int per_sm = c->mma ? 3 : (c->D == 16 && c->R == 1) ? 8 : (c->D == 16 ? (c->occ4 ? 4 : 3) : (c->D == 32 ? 3 : 2));
+        const int per_sm = c->mma ? per_sm_mma : (c->D == 16 && c->R == 1) ? 8 : (c->D == 16 ? (c->occ4 ? 4 : 3) : (c->D == 32 ? 3 : 2));
         const int64_t slots = 148 * per_sm;
         want = cdiv(slots * 3, c->nb);
         double best = 1e30;
@@ -393,11 +399,11 @@ dec_dense_mma_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d
 // mantissa bits (lo = sigma - hi is exact), Z_J = hi + lo as staged; hi*hi + lo*hi + hi*lo.  Tensor
 // cores round the fp32 accumulation towards zero, so the MMA accumulators only run over one
 // 128-key block and are then added into fp32 registers with ordinary rounding.
-template <bool LOSS, bool GRAD>
-__global__ void __launch_bounds__(DEC_THREADS, 3)
+template <bool LOSS, bool GRAD, int MT, int MINB>
+__global__ void __launch_bounds__(DEC_THREADS, MINB)
 dec_dense_mma2_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
                       float *__restrict__ dz_part, double *__restrict__ loss_part) {
-    constexpr int D = 16, MT = 2, JT = 128, JP = JT + 8, FOLD = 32;
+    constexpr int D = 16, JT = 128, JP = JT + 8, FOLD = 32;
     __shared__ __align__(16) uint32_t Zh[JT][D];    // key-major tf32 hi / lo: B operand of S = Z_I Z_J^T
     __shared__ __align__(16) uint32_t Zl[JT][D];
     __shared__ __align__(16) uint32_t ZhT[D][JP];   // dimension-major copies: B operand of P x Z_J
@@ -405,7 +411,7 @@ dec_dense_mma2_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int 
     __shared__ double red[DEC_THREADS / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int64_t i0 = (int64_t)blockIdx.x * DEC_THREADS + warp * (16 * MT);
+    const int64_t i0 = (int64_t)blockIdx.x * (DEC_THREADS / 32 * 16 * MT) + warp * (16 * MT);
     const int64_t jbeg = (int64_t)blockIdx.y * j_chunk;
     const int64_t jend = min(n, jbeg + j_chunk);
 
@@ -774,11 +780,18 @@ static cudaError_t launch_dense_mma(const DecConfig &c, int mode, const float *Z
                                     float *dz_part, double *loss_part, cudaStream_t st) {
     dim3 grid((unsigned)c.nb, (unsigned)c.splits);
     const bool L = mode & GAE_DEC_LOSS, G = mode & GAE_DEC_GRAD;
-    if (c.mma == 2) {
-        if (L && G) dec_dense_mma2_kernel<true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-        else if (L) dec_dense_mma2_kernel<true, false><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-        else dec_dense_mma2_kernel<false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-    } else if (L && G) dec_dense_mma_kernel<true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
+#define GAE_MMA2(MT_, MINB_)                                                                                                        \
+    do {                                                                                                                           \
+        if (L && G) dec_dense_mma2_kernel<true, true, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);   \
+        else if (L) dec_dense_mma2_kernel<true, false, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);  \
+        else dec_dense_mma2_kernel<false, true, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);         \
+    } while (0)
+    if (c.mma == 2) GAE_MMA2(2, 3);
+    else if (c.mma == 3) GAE_MMA2(4, 2);
+    else if (c.mma == 4) GAE_MMA2(1, 5);
+    else if (c.mma == 5) GAE_MMA2(2, 4);
+#undef GAE_MMA2
+    else if (L && G) dec_dense_mma_kernel<true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else if (L) dec_dense_mma_kernel<true, false><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else dec_dense_mma_kernel<false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     count_launch();

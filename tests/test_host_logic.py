@@ -84,11 +84,16 @@ def test_row_bins_host_matches_numpy(lib_built):
     deg[[5, 900]] = [300, 257]
     rowptr = np.zeros(2001, dtype=np.int64)
     np.cumsum(deg, out=rowptr[1:])
-    plan = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256, bins=True)
+    plan = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256, bins=True, sort_mid=False)
     empty, short, mid = (t.numpy() for t in plan.bins)
     assert empty[:plan.struct.n_empty].tolist() == np.flatnonzero(deg == 0).tolist()
     assert short[:plan.struct.n_short].tolist() == np.flatnonzero((deg >= 1) & (deg <= 4)).tolist()
-    assert mid[:plan.struct.n_mid].tolist() == np.flatnonzero((deg > 4) & (deg <= 256)).tolist()
+    want_mid = np.flatnonzero((deg > 4) & (deg <= 256))
+    assert mid[:plan.struct.n_mid].tolist() == want_mid.tolist()
+    # default: the same rows ordered by descending in-degree, ties by row id (stable)
+    plan_s = ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256, bins=True)
+    mid_s = plan_s.bins[2].numpy()[:plan_s.struct.n_mid]
+    assert mid_s.tolist() == want_mid[np.argsort(-deg[want_mid], kind="stable")].tolist()
     assert plan.long_row[:plan.n_long].tolist() == [5, 900]
     assert ops.build_hub_plan(torch.from_numpy(rowptr), seg_len=256).bins is None     # small graph: single pass
 

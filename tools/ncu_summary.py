@@ -22,6 +22,20 @@ METRICS = [
     "smsp__warps_eligible.avg.per_cycle_active", "lts__t_sectors_srcunit_tex_op_read.sum",
     "l1tex__m_xbar2l1tex_read_bytes.sum",
 ]
+COMPUTE_METRICS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "smsp__warps_active.avg.per_cycle_active", "smsp__inst_executed.sum", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+]
 UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -49,8 +63,15 @@ def main():
     ap.add_argument("--algorithmic-bytes", type=int, default=None)
     ap.add_argument("--kernels", type=int, default=0, help="use only the first K kernel rows (0 = all)")
     ap.add_argument("--note", default="")
+    ap.add_argument("--compute", action="store_true", help="pipe-utilisation / stall metrics (compute-bound kernels)")
     args = ap.parse_args()
-    names, units, data = read_raw(args.raw_csv)
+    names, units, data = None, None, []
+    for path in args.raw_csv.split(","):          # several captures with the same metric set: one column each
+        n_, u_, d_ = read_raw(path)
+        if names is None:
+            names, units = n_, u_
+        assert n_ == names, "captures were taken with different metric sets"
+        data += d_
     if args.kernels:
         data = data[:args.kernels]
     col = {n: i for i, n in enumerate(names)}
@@ -61,7 +82,7 @@ def main():
         for key in ("Kernel Name", "Grid Size", "Block Size"):
             if key in col:
                 w.writerow([key, ""] + [r[col[key]] for r in data])
-        for m in METRICS:
+        for m in (COMPUTE_METRICS if args.compute else METRICS):
             if m in col:
                 w.writerow([m, units[col[m]]] + [r[col[m]] for r in data])
             else:
