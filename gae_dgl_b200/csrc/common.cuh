@@ -23,9 +23,7 @@ enum TuningIdx {
     T_SPMM_BINS,         // 1 = use the plan's degree bins when present, 0 = single row pass
     T_DEC_ROWS,          // decoder dense pass: query rows per thread for d <= 16 (1 or 2)
     T_SPMM_SEG_ORDER,    // 1 = walk hub segments in the plan's seg_order (source-id order), 0 = row-major
-    T_SPMM_PERSIST,      // bit 0: persistent row pass, bit 1: persistent hub-segment pass (d <= 64, unweighted)
-    T_DEC_OCC4,          // decoder dense pass, d <= 16, 2 rows per thread: 1 = 128-register build (4 CTAs/SM), 0 = 143 registers (3)
-    T_DEC_MMA,           // decoder dense pass, d <= 16: 1 = dot products as 3xTF32 m16n8k8 MMAs (dec_dense_mma_kernel)
+    T_DEC_MMA,           // decoder dense pass, d <= 16: 1 = both GEMMs as split-precision TF32 MMAs (default), 0 = SIMT FFMA2
     T_COUNT
 };
 

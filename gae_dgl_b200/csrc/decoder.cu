@@ -27,27 +27,17 @@ struct DecConfig {
     int splits;        // key range splits
     int64_t j_chunk;   // key rows per split
     int64_t fin_blocks;
-    bool occ4;         // D = 16, R = 2: 128-register build, 4 CTAs per SM
-    int mma;           // D = 16: 1 = dot products on the tensor cores, 2 = dot products and the gradient GEMM
+    bool mma;          // D = 16: both GEMMs on the tensor cores (dec_dense_mma_kernel)
 };
-
-static inline bool c_occ4_default() { return tuning(T_DEC_OCC4) != 0; }
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (d <= 16) { c->D = 16; c->R = tuning(T_DEC_ROWS) == 1 ? 1 : 2; }
     else if (d <= 32) { c->D = 32; c->R = 1; }
     else if (d <= 64) { c->D = 64; c->R = 1; }
     else return false;
-    c->occ4 = (c_occ4_default() && d <= 16);
-    c->mma = d <= 16 ? tuning(T_DEC_MMA) : 0;
-    if (c->mma < 0 || c->mma > 5) c->mma = 0;
-    int per_sm_mma = 3;
-    int64_t rows_pb = (int64_t)DEC_THREADS * c->R;
-    if (c->mma) {                    // query rows per CTA = 4 warps x 16 MT; resident CTAs per SM by register budget
-        static const int mt[6] = {0, 2, 2, 4, 1, 2}, occ[6] = {0, 3, 3, 2, 5, 4};
-        rows_pb = 64 * mt[c->mma];
-        per_sm_mma = occ[c->mma];
-    }
+    c->mma = d <= 16 && tuning(T_DEC_MMA) != 0;
+    // query rows per CTA: the tensor-core kernel covers 4 warps x 2 m-tiles x 16 rows
+    const int64_t rows_pb = c->mma ? 128 : (int64_t)DEC_THREADS * c->R;
     c->JT = 2048 / c->D;
     c->nb = cdiv(n, rows_pb);
     int64_t max_splits = cdiv(n, c->JT);
@@ -55,9 +45,9 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (want <= 0) {
         // ~3 waves of CTAs (4 resident 128-thread CTAs per SM at 128 registers), then nudge the
         // split count so the last wave is full: wave quantisation cost 20 % at Pubmed size
-        // resident CTAs per SM: R = 1 at 64 registers -> 8; R = 2 -> 3 at 143 registers, 4 with OCC4;
-        // D = 32 / 64 (one row per thread, ~130 / ~250 registers) -> 3 / 2
-        const int per_sm = c->mma ? per_sm_mma : (c->D == 16 && c->R == 1) ? 8 : (c->D == 16 ? (c->occ4 ? 4 : 3) : (c->D == 32 ? 3 : 2));
+        // resident CTAs per SM by register budget: tensor-core kernel 128 registers -> 4; SIMT R = 1 at 64
+        // registers -> 8, R = 2 at 143 -> 3; D = 32 / 64 (one row per thread, ~165 / ~250 registers) -> 3 / 2
+        const int per_sm = c->mma ? 4 : (c->D == 16 && c->R == 1) ? 8 : (c->D == 64 ? 2 : 3);
         const int64_t slots = 148 * per_sm;
         want = cdiv(slots * 3, c->nb);
         double best = 1e30;
@@ -81,10 +71,8 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     return true;
 }
 
-// OCC4 (D = 16, R = 2 only): cap the allocation at 128 registers so that four CTAs (16 warps) are
-// resident per SM instead of three at the 143 registers ptxas takes when left alone.
-template <int D, int R, bool LOSS, bool GRAD, bool OCC4 = false>
-__global__ void __launch_bounds__(DEC_THREADS, (D == 16 && R == 1) ? 8 : (OCC4 ? 4 : 1))
+template <int D, int R, bool LOSS, bool GRAD>
+__global__ void __launch_bounds__(DEC_THREADS, (D == 16 && R == 1) ? 8 : 1)
 dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
                  float *__restrict__ dz_part, double *__restrict__ loss_part) {
     constexpr int JT = 2048 / D;
@@ -178,19 +166,26 @@ dec_dense_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, in
     }
 }
 
-// ---- tensor-core variant of the dense pass (tuning "dec_mma", d <= 16) ------------------------
-// ncu on the SIMT kernel above (Pubmed shape): 16 FFMA2 per pair keep the FP32 pipe busy for the
-// whole launch (1.35 M cycles = 64 pipe cycles per warp-pair-row; two rows per thread, one row per
-// thread, 3 or 4 CTAs/SM all take the same 0.70 ms) -- the kernel sits on the SIMT FP32 roof.  Half
-// of those FMAs are the dot products x_ij = <z_i, z_j>.  Here they go to the tensor cores instead:
-// S = Z_I Z_J^T as m16n8k8 TF32 MMAs with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32
-// accumulate, ~2^-21 relative -- inside the 1e-5 parity budget), six MMAs per 16 x 8 tile of pairs.
-// The softplus / sigmoid chain and the gradient update Z-weighted by sigma stay on the SIMT pipes,
-// working directly on the accumulator fragment: lane (g, t) of a warp holds the pairs
-// (rows g, g+8) x (keys 2t, 2t+1), so it accumulates its two rows' gradient over its quarter of
-// the keys and the four lanes of a row are combined once at the end.  Operands: the query rows'
-// A fragments live in registers for the whole launch (split once); each key tile is split once
-// when it is staged in shared memory (row stride 20 floats: conflict-free fragment loads).
+// ---- tensor-core form of the dense pass (tuning "dec_mma", default for d <= 16) -----------------
+// ncu on the SIMT kernel above (Pubmed shape, 0.70 ms): 16 FFMA2 per pair; one or two rows per
+// thread, three or four CTAs per SM all take the same time -- the FP32 pipe sets it.  The pass is
+// two GEMMs around an element-wise chain (attention-shaped): S = Z_I Z_J^T, then dZ_I = sigma(S) Z_J.
+// Both run here as m16n8k8 TF32 MMAs in SPLIT PRECISION: every operand is hi + lo with hi its TF32
+// rounding, the product is hi*hi + lo*hi + hi*lo with fp32 accumulation (~2^-21 relative, held to
+// the same 1e-5 parity tolerance as the SIMT kernel by the tests).
+//   * Lane (g, t) of a warp holds the pairs (rows g, g+8) x (keys 2t, 2t+1) of a 16 x 8 tile of S.
+//     The contraction index of an MMA may be permuted freely as long as A and B agree, so with
+//     slot t = key 2t and slot t+4 = key 2t+1 that accumulator fragment IS the A fragment of the
+//     second GEMM: sigma goes from the softplus chain into the next MMA without a shuffle.  The same
+//     trick on the embedding dimension makes a lane's four B values one LDS.128.
+//   * The query rows' A fragments are split once and stay in registers for the whole launch; a key
+//     tile is split once when it is staged in shared memory, key-major for S and dimension-major
+//     for the gradient GEMM; sigma is split by masking its low 13 mantissa bits (lo is exact).
+//   * Tensor cores round the fp32 accumulation towards zero: the gradient MMAs accumulate over one
+//     128-key block only and are then added into ordinary fp32 registers.
+//   * Loss: sum softplus(x) = sum max(x,0) + ln prod (1 + e^-|x|); a product of 64 factors in (1,2]
+//     cannot overflow, so one lg2 per 64 pairs replaces one per pair.
+// The dz_part / loss_part layouts are those of dec_dense_kernel; dec_finalize_kernel is shared.
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -203,207 +198,10 @@ __device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (
 }
 
 template <bool LOSS, bool GRAD>
-__global__ void __launch_bounds__(DEC_THREADS, 3)
+__global__ void __launch_bounds__(DEC_THREADS, 4)
 dec_dense_mma_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
-                     float *__restrict__ dz_part, double *__restrict__ loss_part) {
-    constexpr int D = 16, MT = 2, JT = 128, LDF = 20, FOLD = 32;
-    __shared__ __align__(16) float Zs[JT][LDF];     // fp32 key rows (gradient operand), stride 20: conflict-free row reads
-    __shared__ __align__(16) uint32_t Zh[JT][D];    // tf32 "hi" part, stride 16: conflict-free 128-bit fragment reads
-    __shared__ __align__(16) uint32_t Zl[JT][D];    // tf32 "lo" part (x - hi)
-    __shared__ double red[DEC_THREADS / 32];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int64_t i0 = (int64_t)blockIdx.x * DEC_THREADS + warp * (16 * MT);
-    const int64_t jbeg = (int64_t)blockIdx.y * j_chunk;
-    const int64_t jend = min(n, jbeg + j_chunk);
-
-    // The contraction index may be permuted freely as long as A and B agree: k-step ks, slot t
-    // stands for dimension 4t + 2ks and slot t + 4 for 4t + 2ks + 1, so that a lane's four B values
-    // of both k-steps are the 16 contiguous bytes [4t, 4t + 4) of a key row (one LDS.128).
-    uint32_t ah[MT][2][4], al[MT][2][4];
-    bool rv[MT][2];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        const int64_t r0 = i0 + m * 16 + g, r1 = r0 + 8;
-        rv[m][0] = r0 < n;
-        rv[m][1] = r1 < n;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int c0 = 4 * t + 2 * ks, c1 = c0 + 1;
-            const float x[4] = {(rv[m][0] && c0 < d) ? __ldg(Zd + r0 * ldz + c0) : 0.f,
-                                (rv[m][1] && c0 < d) ? __ldg(Zd + r1 * ldz + c0) : 0.f,
-                                (rv[m][0] && c1 < d) ? __ldg(Zd + r0 * ldz + c1) : 0.f,
-                                (rv[m][1] && c1 < d) ? __ldg(Zd + r1 * ldz + c1) : 0.f};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ah[m][ks][q] = to_tf32(x[q]);
-                al[m][ks][q] = to_tf32(x[q] - __uint_as_float(ah[m][ks][q]));
-            }
-        }
-    }
-    float2 acc[MT][2][D / 2];
-    // loss: sum_j softplus(x) = sum_j max(x,0) + log prod_j (1 + e^-|x|); the product of FOLD*2 factors
-    // in (1,2] stays below 2^64, so one lg2 per 64 pairs replaces one per pair
-    float msum[MT][2], lsum[MT][2], prod[MT][2];
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            msum[m][h] = 0.f;
-            lsum[m][h] = 0.f;
-            prod[m][h] = 1.f;
-#pragma unroll
-            for (int k = 0; k < D / 2; ++k) acc[m][h][k] = make_float2(0.f, 0.f);
-        }
-    int tiles = 0, pads = 0;
-
-    for (int64_t j0 = jbeg; j0 < jend; j0 += JT) {
-        const int jcount = (int)min((int64_t)JT, jend - j0);
-        __syncthreads();
-        for (int idx = tid; idx < JT * D; idx += DEC_THREADS) {
-            const int jj = idx / D, k = idx % D;
-            const float x = (jj < jcount && k < d) ? __ldg(Zd + (j0 + jj) * ldz + k) : 0.f;
-            const uint32_t hi = to_tf32(x);
-            Zs[jj][k] = x;
-            Zh[jj][k] = hi;
-            Zl[jj][k] = to_tf32(x - __uint_as_float(hi));
-        }
-        __syncthreads();
-        // keys past jcount inside the last 8-key tile are zero rows: x = 0 exactly, they add nothing to
-        // the gradient and exactly ln 2 each to the loss, which is taken off again at the end
-        if (LOSS) pads += min(2, max(0, ((jcount + 7) & ~7) - jcount - (6 - 2 * t)));
-        for (int jt = 0; jt < jcount; jt += 8) {
-            const uint4 vh = *reinterpret_cast<const uint4 *>(&Zh[jt + g][4 * t]);
-            const uint4 vl = *reinterpret_cast<const uint4 *>(&Zl[jt + g][4 * t]);
-            float cs[MT][4], cb[MT][4];
-#pragma unroll
-            for (int m = 0; m < MT; ++m)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) cs[m][e] = cb[m][e] = 0.f;
-            // two accumulators per m-tile (small terms / hi*hi), interleaved: no back-to-back dependent MMAs
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cs[m], al[m][0], vh.x, vh.y);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cb[m], ah[m][0], vh.x, vh.y);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cs[m], ah[m][0], vl.x, vl.y);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cb[m], ah[m][1], vh.z, vh.w);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cs[m], al[m][1], vh.z, vh.w);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_m16n8k8_tf32(cs[m], ah[m][1], vl.z, vl.w);
-            // the two key rows this lane's accumulator columns belong to (keys 2t, 2t+1), fp32
-            float2 zj[2][D / 2];
-            if (GRAD) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int k4 = 0; k4 < D / 4; ++k4) {
-                        const float4 v = *reinterpret_cast<const float4 *>(&Zs[jt + 2 * t + q][k4 * 4]);
-                        zj[q][k4 * 2 + 0] = make_float2(v.x, v.y);
-                        zj[q][k4 * 2 + 1] = make_float2(v.z, v.w);
-                    }
-            }
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                // e = 0: (row g, key 2t)  1: (row g, key 2t+1)  2: (row g+8, key 2t)  3: (row g+8, key 2t+1)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int h = e >> 1, q = e & 1;
-                    const float x = cs[m][e] + cb[m][e];
-                    float ex, r;
-                    const float a = -fabsf(x) * 1.4426950408889634f;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a));
-                    const float one_e = 1.0f + ex;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(one_e));
-                    if (LOSS) {
-                        msum[m][h] += fmaxf(x, 0.f);
-                        prod[m][h] *= one_e;
-                    }
-                    if (GRAD) {
-                        const float sg = (x >= 0.f) ? r : ex * r;
-                        const float2 sg2 = make_float2(sg, sg);
-#pragma unroll
-                        for (int k = 0; k < D / 2; ++k) acc[m][h][k] = __ffma2_rn(sg2, zj[q][k], acc[m][h][k]);
-                    }
-                }
-            }
-            if (LOSS && (++tiles & (FOLD - 1)) == 0) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float l2;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod[m][h]));
-                        lsum[m][h] += l2;
-                        prod[m][h] = 1.f;
-                    }
-            }
-        }
-    }
-
-    if (GRAD) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int k = 0; k < D / 2; ++k) {      // the four lanes of a row hold disjoint key subsets
-                    float2 v = acc[m][h][k];
-                    v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
-                    v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
-                    v.x += __shfl_xor_sync(0xffffffffu, v.x, 2);
-                    v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
-                    acc[m][h][k] = v;
-                }
-                if (rv[m][h]) {                        // lane t stores columns 4t .. 4t+3
-                    const int64_t i = i0 + m * 16 + h * 8 + g;
-                    const float2 lo = t == 0 ? acc[m][h][0] : t == 1 ? acc[m][h][2] : t == 2 ? acc[m][h][4] : acc[m][h][6];
-                    const float2 hi = t == 0 ? acc[m][h][1] : t == 1 ? acc[m][h][3] : t == 2 ? acc[m][h][5] : acc[m][h][7];
-                    float4 *o = reinterpret_cast<float4 *>(dz_part + ((int64_t)blockIdx.y * n + i) * D) + t;
-                    *o = make_float4(lo.x, lo.y, hi.x, hi.y);
-                }
-            }
-    }
-    if (LOSS) {
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float l2;
-                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod[m][h]));
-                // log2 terms (minus one per padded key: log2(1 + e^0) = 1) -> natural log
-                const double row = (double)msum[m][h] + ((double)(lsum[m][h] + l2) - (double)pads) * 0.6931471805599453;
-                s += rv[m][h] ? row : 0.0;
-            }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) red[warp] = s;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < DEC_THREADS / 32; ++w) tot += red[w];
-            loss_part[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
-        }
-    }
-}
-
-// ---- both GEMMs on the tensor cores (tuning "dec_mma" = 2) --------------------------------------
-// The gradient's dense term dZ_i = sum_j sigma(x_ij) z_j is the second GEMM of this attention-shaped
-// pass, P (pairs) x Z_J.  The accumulator fragment of S = Z_I Z_J^T is already laid out as the A
-// operand of the next m16n8k8 MMA once the contraction index (the key) is permuted the same way on
-// both operands (slot t = key 2t, slot t+4 = key 2t+1), so sigma goes from the softplus chain straight
-// into the MMA without a shuffle.  Split precision again: sigma = hi + lo by masking the low 13
-// mantissa bits (lo = sigma - hi is exact), Z_J = hi + lo as staged; hi*hi + lo*hi + hi*lo.  Tensor
-// cores round the fp32 accumulation towards zero, so the MMA accumulators only run over one
-// 128-key block and are then added into fp32 registers with ordinary rounding.
-template <bool LOSS, bool GRAD, int MT, int MINB>
-__global__ void __launch_bounds__(DEC_THREADS, MINB)
-dec_dense_mma2_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d, int64_t j_chunk,
                       float *__restrict__ dz_part, double *__restrict__ loss_part) {
-    constexpr int D = 16, JT = 128, JP = JT + 8, FOLD = 32;
+    constexpr int D = 16, MT = 2, JT = 128, JP = JT + 8, FOLD = 32;
     __shared__ __align__(16) uint32_t Zh[JT][D];    // key-major tf32 hi / lo: B operand of S = Z_I Z_J^T
     __shared__ __align__(16) uint32_t Zl[JT][D];
     __shared__ __align__(16) uint32_t ZhT[D][JP];   // dimension-major copies: B operand of P x Z_J
@@ -780,18 +578,7 @@ static cudaError_t launch_dense_mma(const DecConfig &c, int mode, const float *Z
                                     float *dz_part, double *loss_part, cudaStream_t st) {
     dim3 grid((unsigned)c.nb, (unsigned)c.splits);
     const bool L = mode & GAE_DEC_LOSS, G = mode & GAE_DEC_GRAD;
-#define GAE_MMA2(MT_, MINB_)                                                                                                        \
-    do {                                                                                                                           \
-        if (L && G) dec_dense_mma2_kernel<true, true, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);   \
-        else if (L) dec_dense_mma2_kernel<true, false, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);  \
-        else dec_dense_mma2_kernel<false, true, MT_, MINB_><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);         \
-    } while (0)
-    if (c.mma == 2) GAE_MMA2(2, 3);
-    else if (c.mma == 3) GAE_MMA2(4, 2);
-    else if (c.mma == 4) GAE_MMA2(1, 5);
-    else if (c.mma == 5) GAE_MMA2(2, 4);
-#undef GAE_MMA2
-    else if (L && G) dec_dense_mma_kernel<true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
+    if (L && G) dec_dense_mma_kernel<true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else if (L) dec_dense_mma_kernel<true, false><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else dec_dense_mma_kernel<false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     count_launch();
@@ -803,13 +590,6 @@ static cudaError_t launch_dense(const DecConfig &c, int mode, const float *Zd, i
                                 float *dz_part, double *loss_part, cudaStream_t st) {
     dim3 grid((unsigned)c.nb, (unsigned)c.splits);
     const bool L = mode & GAE_DEC_LOSS, G = mode & GAE_DEC_GRAD;
-    if constexpr (D == 16 && R == 2) if (c.occ4) {
-        if (L && G) dec_dense_kernel<D, R, true, true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-        else if (L) dec_dense_kernel<D, R, true, false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-        else dec_dense_kernel<D, R, false, true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
-        count_launch();
-        return cudaGetLastError();
-    }
     if (L && G) dec_dense_kernel<D, R, true, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else if (L) dec_dense_kernel<D, R, true, false><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);
     else dec_dense_kernel<D, R, false, true><<<grid, DEC_THREADS, 0, st>>>(Zd, ldz, n, d, c.j_chunk, dz_part, loss_part);

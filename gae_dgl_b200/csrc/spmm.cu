@@ -17,8 +17,6 @@
 // launched over fixed-length segments that write partial rows, followed by a tiny ordered
 // reduce -- deterministic two-stage reduction instead of atomics.  Empty rows are written
 // as zeros by the row kernel.
-#include <algorithm>
-
 #include "common.cuh"
 
 namespace gae {
@@ -168,115 +166,6 @@ __global__ void __launch_bounds__(128, MINB) spmm_vec_kernel(const SpmmArgs a) {
     }
 }
 
-// Persistent variant of the row / segment pass (tuning "spmm_persist", bit 0 = rows, bit 1 = hub
-// segments).  ncu on C4 showed the warp-per-row kernel 58 % occupied and neither L2- nor
-// DRAM-bound: half a million two-warp CTAs that live for one ~35-edge row each spend their time in
-// the start-up chain row_list -> rowptr -> col -> X (four dependent memory latencies) and in CTA
-// turnover.  Here the grid is sized to the machine (MINB CTAs per SM, all resident for the whole
-// launch) and every warp walks items w, 2W-1-w, 2W+w, ... (serpentine over rounds of W warps, so
-// that with the items sorted by length the per-warp edge totals even out).  The row id is loaded
-// two rounds ahead and the row bounds one round ahead: when a warp finishes a row the next one's
-// descriptor is already in registers and only col -> X remains on the critical path.
-// The per-row summation (edge e to lane group e mod GPR, U gathers in flight, xor-shuffle tree)
-// is the same as in spmm_vec_kernel: results are bit-identical.
-__device__ __forceinline__ long long ld_i64(const int64_t *p) {
-    long long r;
-    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(r) : "l"(p));
-    return r;
-}
-
-template <int LPR, int U, bool SEG, int MINB>
-__global__ void __launch_bounds__(128, MINB) spmm_persist_kernel(const SpmmArgs a) {
-    constexpr int GPR = 32 / LPR;  // the whole warp works on one item
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % LPR;
-    const int phase = lane / LPR;
-    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t n = a.n_items;
-    const int d = a.d;
-    const bool colok = sub * 4 < d;
-    const float *xb = a.X + (colok ? sub : 0) * 4;
-    const int ldx = (int)a.ldx;
-    const int64_t rounds = (n + W - 1) / W;
-
-    auto item_at = [&](int64_t k) -> int64_t {
-        const int64_t it = k * W + ((k & 1) ? (W - 1 - w) : w);
-        return (k < rounds && it < n) ? it : -1;
-    };
-    // item -> id (row id, or segment id) with an optional indirection list
-    auto id_of = [&](int64_t it) -> int {
-        if (it < 0) return -1;
-        const int32_t *list = SEG ? a.seg_order : a.row_list;
-        return list ? ld_idx(list + it) : (int)it;
-    };
-
-    int id0 = id_of(item_at(0));
-    int id1 = id_of(item_at(1));
-    long long s0 = 0;
-    int len0 = 0;
-    if (!SEG && id0 >= 0) {
-        s0 = ld_i64(a.rowptr + id0);
-        len0 = (int)(ld_i64(a.rowptr + id0 + 1) - s0);
-    }
-    for (int64_t k = 0; k < rounds; ++k) {
-        const int id2 = id_of(item_at(k + 2));
-        long long s1 = 0;
-        int len1 = 0;
-        if (!SEG && id1 >= 0) {
-            s1 = ld_i64(a.rowptr + id1);
-            len1 = (int)(ld_i64(a.rowptr + id1 + 1) - s1);
-        }
-        float *out = nullptr;
-        if (SEG) {
-            len0 = 0;
-            if (id0 >= 0) {  // 512-edge segments amortise this chain; no prefetch needed
-                const int32_t kk = __ldg(a.seg_row + id0);
-                const int64_t row = __ldg(a.long_row + kk);
-                const int64_t sidx = (int64_t)id0 - __ldg(a.long_seg_ptr + kk);
-                const int64_t r0 = __ldg(a.rowptr + row), r1 = __ldg(a.rowptr + row + 1);
-                s0 = r0 + sidx * (int64_t)a.seg_len;
-                len0 = (int)(min((int64_t)s0 + a.seg_len, r1) - s0);
-                out = a.Y + (int64_t)id0 * a.ldy;
-            }
-        } else if (id0 >= 0) {
-            out = a.Y + (int64_t)id0 * a.ldy;
-            if (a.seg_len > 0 && len0 > a.seg_len) out = nullptr;  // hub row: owned by the segment pass
-        }
-        if (out != nullptr) {  // warp-uniform
-            float4 acc = f4_zero();
-            const int32_t *cp = a.col + s0;
-            for (int i = phase; i < len0; i += GPR * U) {
-                int c[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) c[u] = ld_idx(cp + min(i + u * GPR, len0 - 1));
-                float4 v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = gather_f4<0>(xb + (int64_t)c[u] * ldx, 0);
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (i + u * GPR < len0) f4_add(acc, v[u]);
-            }
-            if (GPR > 1) {
-                __syncwarp();
-#pragma unroll
-                for (int off = LPR; off < 32; off <<= 1) f4_add(acc, f4_shfl_xor(acc, off));
-            }
-            if (phase == 0 && colok) {
-                float *o = out + sub * 4;
-                if (sub * 4 + 4 <= d) {
-                    if (!SEG && a.accumulate) f4_add(acc, *reinterpret_cast<const float4 *>(o));
-                    *reinterpret_cast<float4 *>(o) = acc;
-                } else {
-                    const float t[4] = {acc.x, acc.y, acc.z, acc.w};
-                    for (int q = 0; sub * 4 + q < d; ++q) o[q] = (!SEG && a.accumulate) ? o[q] + t[q] : t[q];
-                }
-            }
-        }
-        id0 = id1; s0 = s1; len0 = len1; id1 = id2;
-    }
-}
-
 // Short rows (1..U in-edges): LPR lanes x CPL float4 cover a row, 32/LPR rows per warp, every
 // gather of the row in flight at once (U x CPL 128-bit loads per lane) -- one latency per row
 // instead of a warp and a dependent chain per row.
@@ -409,42 +298,6 @@ static cudaError_t launch_vec(const SpmmArgs &a, int rows_per_warp, int unroll, 
     return launch_shape<32, 1, SEG>(a, unroll, cache, block, st);
 }
 
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
-
-// d <= 64, unweighted, plain caching; returns false when the shape is not covered.
-// Two register budgets: U = 4 gathers in flight at 48 registers (40 warps/SM) or U = 8 at 64 (32 warps/SM).
-template <int LPR, bool SEG>
-static void launch_persist_lpr(const SpmmArgs &a, int unroll, cudaStream_t st) {
-    const int64_t want = cdiv(a.n_items, 4);
-    if (unroll >= 8) {
-        const int64_t blocks = std::min<int64_t>(want, (int64_t)sm_count() * 8);
-        spmm_persist_kernel<LPR, 8, SEG, 8><<<(unsigned)blocks, 128, 0, st>>>(a);
-    } else {
-        const int64_t blocks = std::min<int64_t>(want, (int64_t)sm_count() * 10);
-        spmm_persist_kernel<LPR, 4, SEG, 10><<<(unsigned)blocks, 128, 0, st>>>(a);
-    }
-}
-
-template <bool SEG>
-static bool launch_persist(const SpmmArgs &a, int unroll, cudaStream_t st, cudaError_t *err) {
-    const int d4 = (a.d + 3) / 4;
-    if (a.vals || d4 > 16 || a.n_items <= 0) return false;
-    if (d4 <= 4) launch_persist_lpr<4, SEG>(a, unroll, st);
-    else if (d4 <= 8) launch_persist_lpr<8, SEG>(a, unroll, st);
-    else launch_persist_lpr<16, SEG>(a, unroll, st);
-    count_launch();
-    *err = cudaGetLastError();
-    return true;
-}
-
 cudaError_t spmm_stream_launch(const StreamArgs &a, int d, bool seg, int stages, int mode, cudaStream_t st);
 
 }  // namespace gae
@@ -478,7 +331,6 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     const int unroll = tuning(T_SPMM_UNROLL);
     const int cache = tuning(T_SPMM_CACHE);
     const int rpw = tuning(T_SPMM_ROWS_PER_WARP);
-    const int persist = tuning(T_SPMM_PERSIST);
 
     if (!vec) {
         // correctness-only path; hub rows are not split (one warp each)
@@ -529,14 +381,10 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
         if (plan->n_mid > 0) {
             SpmmArgs md = a;
             md.row_list = plan->mid_rows; md.n_items = plan->n_mid;
-            cudaError_t e = cudaSuccess;
-            if ((persist & 1) && cache == 0 && launch_persist<false>(md, unroll, st, &e)) GAE_CUDA(e);
-            else GAE_CUDA(launch_vec<false>(md, rpw, unroll, cache, block, st));
+            GAE_CUDA(launch_vec<false>(md, rpw, unroll, cache, block, st));
         }
     } else {
-        cudaError_t e = cudaSuccess;
-        if ((persist & 1) && cache == 0 && launch_persist<false>(a, unroll, st, &e)) GAE_CUDA(e);
-        else GAE_CUDA(launch_vec<false>(a, rpw, unroll, cache, block, st));
+        GAE_CUDA(launch_vec<false>(a, rpw, unroll, cache, block, st));
     }
     if (use_plan) {
         const int64_t ldp = (int64_t)((d + 3) / 4) * 4;
@@ -545,9 +393,7 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
         s.long_row = plan->long_row; s.long_seg_ptr = plan->long_seg_ptr; s.seg_row = plan->seg_row;
         s.row_list = nullptr;
         s.seg_order = tuning(T_SPMM_SEG_ORDER) ? plan->seg_order : nullptr;
-        cudaError_t e = cudaSuccess;
-        if ((persist & 2) && cache == 0 && launch_persist<true>(s, unroll, st, &e)) GAE_CUDA(e);
-        else GAE_CUDA(launch_vec<true>(s, 1, unroll, cache, block, st));
+        GAE_CUDA(launch_vec<true>(s, 1, unroll, cache, block, st));
         const int64_t threads = plan->n_long * ((d + 3) / 4);
         spmm_hub_reduce_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(
             partial_ws, ldp, plan->long_row, plan->long_seg_ptr, plan->n_long, Y, ldy, d, accumulate);

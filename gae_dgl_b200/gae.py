@@ -12,6 +12,7 @@ from __future__ import annotations
 
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -119,13 +120,18 @@ def pos_weight_of(g: DGLGraph, transductive: bool = False, per_graph: bool = Fal
     below 2^24 edges; the arithmetic below repeats the reference's fp32 tensor ops.
     per_graph: the pair count is sum_k n_k^2 (block-diagonal decoder) instead of N^2."""
     n = g.number_of_nodes()
-    adj_sum = torch.tensor(float(g.number_of_edges()), dtype=torch.float32)
+    # numpy float32 scalars perform the same IEEE single-precision operations as the 0-dim fp32
+    # tensors of the reference expression (checked against torch in tests/test_host_logic.py) at a
+    # fraction of the host cost -- this runs once per step in the inductive loop
+    adj_sum = np.float32(g.number_of_edges())
     if per_graph:
         pairs = g.block_ranges()[2]
-        return float((pairs - adj_sum) / adj_sum)
+        return float((np.float32(pairs) - adj_sum) / adj_sum)
     if transductive:
-        return float(torch.Tensor([float(n * n - adj_sum) / adj_sum])[0])
-    return float((n * n - adj_sum) / adj_sum)
+        # `python_float / tensor` is Tensor.__rtruediv__ = tensor.reciprocal() * python_float: an fp32
+        # reciprocal and an fp32 multiply (train_transductive.py:60), not an fp32 division
+        return float((np.float32(1.0) / adj_sum) * (np.float32(n * n) - adj_sum))
+    return float((np.float32(n * n) - adj_sum) / adj_sum)
 
 
 class GAE(nn.Module):

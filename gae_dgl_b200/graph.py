@@ -437,7 +437,7 @@ def batch(graphs: Sequence[DGLGraph], device=None) -> DGLGraph:
             ep_dev = torch.from_numpy(edge_ptr).to(device)
             rc = lib.gae_batch_offset_cols_i32(ctypes.c_void_p(col_dev.data_ptr()), ctypes.c_void_p(ep_dev.data_ptr()),
                                                ctypes.c_void_p(off_dev.data_ptr()), len(graphs), col_dev.numel(),
-                                               torch.cuda.current_stream().cuda_stream)
+                                               ops._stream())
             _lib.check(rc, "gae_batch_offset_cols_i32")
             # molecular batches have max degree 4: no hub rows, skip the host plan scan
             out.append(CSR(rp_dev, col_dev, None))
@@ -548,7 +548,7 @@ class PackedGraphDataset:
                                         self.feat_all.stride(0) if feat_out is not None else 0,
                                         self.feat_all.shape[1] if feat_out is not None else 0, p(feat_out),
                                         feat_out.stride(0) if feat_out is not None else 0,
-                                        torch.cuda.current_stream().cuda_stream)
+                                        ops._stream())
             _lib.check(rc, "gae_batch_assemble")
             if feat_out is not None:
                 bg.ndata[self.feature_key] = feat_out

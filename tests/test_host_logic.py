@@ -4,6 +4,7 @@ import ctypes
 import os
 import pickle
 import re
+import types
 
 import numpy as np
 import pytest
@@ -304,3 +305,18 @@ def test_planetoid_loader(tmp_path):
     a = TT.build_parser().parse_args(["--dataset", "citeseer", "--data_dir", str(tmp_path)])
     feats, g2 = TT.load_data(a)
     assert feats.shape == (10, 7) and g2.number_of_edges() == len(want)
+
+
+def test_pos_weight_matches_the_reference_expressions_bit_for_bit():
+    """gae.pos_weight_of evaluates train_inductive.py:46 / train_transductive.py:60 with numpy float32
+    scalars; the reference evaluates them with 0-dim fp32 tensors (the transductive one through
+    Tensor.__rtruediv__, i.e. reciprocal * scalar).  Same IEEE operations -> identical floats."""
+    import random
+    random.seed(0)
+    for _ in range(3000):
+        n = random.randint(2, 40000)
+        e = random.randint(1, min(n * n - 1, 3_000_000))
+        g = types.SimpleNamespace(number_of_nodes=lambda n=n: n, number_of_edges=lambda e=e: e)
+        adj_sum = torch.tensor(float(e), dtype=torch.float32)          # == adj.sum() of a 0/1(/2..) fp32 matrix
+        assert G.pos_weight_of(g) == float((n * n - adj_sum) / adj_sum)
+        assert G.pos_weight_of(g, transductive=True) == float(torch.Tensor([float(n * n - adj_sum) / adj_sum])[0])

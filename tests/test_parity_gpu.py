@@ -69,15 +69,9 @@ def test_spmm_parity(cuda, d, rows_per_warp):
                 Y = ops.spmm(rp, cl, X.to(cuda), plan, out=Y)
                 assert rel_err(Y, ref) < TOL, (d, seg_len, bins, unroll)
                 assert float(Y[n - 5:].abs().max()) == 0.0          # empty rows are zeros
-                if rows_per_warp == 1:      # persistent row / segment passes: same order of adds -> same bits
-                    _lib.set_tuning("spmm_persist", 3)
-                    Yp = ops.spmm(rp, cl, X.to(cuda), plan)
-                    _lib.set_tuning("spmm_persist", 0)
-                    assert torch.equal(Yp, Y), (d, seg_len, bins, unroll)
     finally:
         _lib.set_tuning("spmm_rows_per_warp", 1)
         _lib.set_tuning("spmm_unroll", 4)
-        _lib.set_tuning("spmm_persist", 0)
 
 
 @pytest.mark.parametrize("cache", [0, 1, 2])
@@ -96,22 +90,6 @@ def test_spmm_cache_variants_bit_identical(cuda, cache):
         _lib.set_tuning("spmm_cache", 0)
     assert torch.equal(Y, base)               # same summation order -> same bits
     assert torch.equal(ops.spmm(rp, cl, X, plan), base)   # run-to-run deterministic
-    if cache == 0:     # persistent passes on the un-binned plan (all rows, hub rows skipped) and without a plan
-        try:
-            for persist in (1, 2, 3):
-                _lib.set_tuning("spmm_persist", persist)
-                assert torch.equal(ops.spmm(rp, cl, X, plan), base), persist
-            no_plan = ops.spmm(rp, cl, X)
-            _lib.set_tuning("spmm_persist", 0)
-            assert torch.equal(ops.spmm(rp, cl, X), no_plan)
-            out0 = base.clone()
-            ops.spmm(rp, cl, X, plan, out=out0, accumulate=True)
-            _lib.set_tuning("spmm_persist", 3)
-            out1 = base.clone()
-            ops.spmm(rp, cl, X, plan, out=out1, accumulate=True)
-            assert torch.equal(out0, out1)
-        finally:
-            _lib.set_tuning("spmm_persist", 0)
 
 
 @pytest.mark.parametrize("variant", [1, 2])
@@ -221,26 +199,22 @@ def test_spmm_large_properties(cuda):
     from oracle import c_spmm
     ref = c_spmm.spmm_f64acc(c.rowptr.cpu().numpy(), c.col.cpu().numpy(), X.cpu().numpy())
     assert rel_err(YX, torch.from_numpy(ref)) < TOL
-    # persistent passes (many rounds per warp at this size), with and without the degree-sorted
-    # mid-row list: identical bits to the default launch
+    # the degree-sorted mid-row list (default) and the row-ordered one give identical bits, for both unrolls
     try:
         for sort_mid in (False, True):
             plan2 = ops.build_hub_plan(c.rowptr, c.plan.seg_len, sort_mid=sort_mid)
             ops.order_segments_by_source(plan2, c.rowptr, c.col)
             assert plan2.bins is not None
+            mid = plan2.bins[2][:int(plan2.struct.n_mid)].long()
             if sort_mid:
-                mid = plan2.bins[2][:int(plan2.struct.n_mid)].long()
                 dm = deg[mid]
                 assert bool((dm[:-1] >= dm[1:]).all())
-                assert torch.equal(torch.sort(mid).values,
-                                   torch.sort(c.plan.bins[2][:int(c.plan.struct.n_mid)].long()).values)
-            for persist in (0, 1, 2, 3):
-                for unroll in (4, 8):
-                    _lib.set_tuning("spmm_persist", persist)
-                    _lib.set_tuning("spmm_unroll", unroll)
-                    assert torch.equal(ops.spmm(c.rowptr, c.col, X, plan2), YX), (sort_mid, persist, unroll)
+            assert torch.equal(torch.sort(mid).values,
+                               torch.sort(c.plan.bins[2][:int(c.plan.struct.n_mid)].long()).values)
+            for unroll in (4, 8):
+                _lib.set_tuning("spmm_unroll", unroll)
+                assert torch.equal(ops.spmm(c.rowptr, c.col, X, plan2), YX), (sort_mid, unroll)
     finally:
-        _lib.set_tuning("spmm_persist", 0)
         _lib.set_tuning("spmm_unroll", 4)
 
 
@@ -303,24 +277,21 @@ def test_decoder_loss_and_grad_parity(cuda, n, d, e):
     assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
     scale = float(Zr.grad.abs().max())
     assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * scale
-    if d <= 16:     # every variant of the dense pass (SIMT, SIMT at 128 registers, tensor-core ones): same tolerance
+    if d <= 16:     # both forms of the dense pass (tensor-core default, SIMT), every loss / gradient mode
         default_mma = _lib.get_tuning("dec_mma")
+        assert default_mma == 1
         try:
-            for knob, val in (("dec_mma", 0), ("dec_mma", 1), ("dec_mma", 2), ("dec_mma", 3), ("dec_mma", 4), ("dec_mma", 5),
-                              ("dec_occ4", 1)):
-                _lib.set_tuning("dec_mma", 0)
-                _lib.set_tuning(knob, val)
+            for mma in (0, 1):
+                _lib.set_tuning("dec_mma", mma)
                 for wl, wg in ((True, True), (True, False), (False, True)):
                     l2, dZ2 = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), pw,
                                               want_loss=wl, want_grad=wg)
                     if wl:
-                        assert abs(float(l2) - float(ref)) < TOL * abs(float(ref)), (knob, val)
+                        assert abs(float(l2) - float(ref)) < TOL * abs(float(ref)), mma
                     if wg:
-                        assert float((dZ2.double().cpu() - Zr.grad).abs().max()) < TOL * scale, (knob, val)
-                _lib.set_tuning(knob, 0)
+                        assert float((dZ2.double().cpu() - Zr.grad).abs().max()) < TOL * scale, mma
         finally:
             _lib.set_tuning("dec_mma", default_mma)
-            _lib.set_tuning("dec_occ4", 0)
     loss_only, none = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), None, None, pw, True, False)
     assert none is None and float(loss_only) == float(loss)
     X = ops.decoder_logits(Z.to(cuda))

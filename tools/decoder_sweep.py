@@ -18,9 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--rows", type=str, default="1,2")
-    ap.add_argument("--occ4", type=str, default="0,1")
     ap.add_argument("--splits", type=str, default="0")
-    ap.add_argument("--mma", type=str, default="0,1,2")
+    ap.add_argument("--mma", type=str, default="0,1")
     ap.add_argument("--out", type=str, default="")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -32,13 +31,12 @@ def main():
         n = g.number_of_nodes()
         Z = (0.3 * torch.randn(n, 16, generator=torch.Generator().manual_seed(0))).to(dev)
         ref = None
-        for rows, occ4, splits, mma in itertools.product(*[[int(v) for v in s.split(",")]
-                                                           for s in (args.rows, args.occ4, args.splits, args.mma)]):
-            if mma and (rows != 2 or occ4):
+        for rows, splits, mma in itertools.product(*[[int(v) for v in s.split(",")]
+                                                     for s in (args.rows, args.splits, args.mma)]):
+            if mma and rows != 2:
                 continue
             _lib.set_tuning("dec_mma", mma)
             _lib.set_tuning("dec_rows", rows)
-            _lib.set_tuning("dec_occ4", occ4)
             _lib.set_tuning("dec_splits", splits)
             for _ in range(3):
                 loss, dz = ops.decoder_bce(Z, c.rowptr, c.col, t.rowptr, t.col, 100.0, True, True)
@@ -52,7 +50,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.iters
             if ref is None:
                 ref = (float(loss), dz.clone())
-            r = {"graph": name, "n": n, "dec_rows": rows, "dec_occ4": occ4, "dec_splits": splits, "dec_mma": mma, "ms": ms,
+            r = {"graph": name, "n": n, "dec_rows": rows, "dec_splits": splits, "dec_mma": mma, "ms": ms,
                  "pairs_per_s": n * n / (ms * 1e-3), "loss": float(loss), "loss_diff_vs_first": abs(float(loss) - ref[0]),
                  "grad_maxdiff_vs_first": float((dz - ref[1]).abs().max())}
             results.append(r)

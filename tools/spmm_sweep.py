@@ -36,7 +36,6 @@ def main():
     ap.add_argument("--bins", type=str, default="1")
     ap.add_argument("--stages", type=str, default="2,3,4")
     ap.add_argument("--out", type=str, default="")
-    ap.add_argument("--persist", type=str, default="0", help="spmm_persist values (bit 0 rows, bit 1 hub segments)")
     ap.add_argument("--mid-sort", type=str, default="0", help="0 / 1: degree-sorted mid-row list")
     ap.add_argument("--seg-orders", type=str, default="0,1")
     args = ap.parse_args()
@@ -102,10 +101,9 @@ def main():
         _lib.set_tuning("spmm_variant", 0)
         if "0" not in args.variants.split(","):
             continue
-        for block, unroll, cache, rpw, bins, so, persist in itertools.product(
+        for block, unroll, cache, rpw, bins, so in itertools.product(
                 blocks, unrolls, caches, (1,), [int(b) for b in args.bins.split(",")],
-                [int(v) for v in args.seg_orders.split(",")], [int(v) for v in args.persist.split(",")]):
-            _lib.set_tuning("spmm_persist", persist)
+                [int(v) for v in args.seg_orders.split(",")]):
             _lib.set_tuning("spmm_bins", bins)
             _lib.set_tuning("spmm_seg_order", so)
             _lib.set_tuning("spmm_block", block)
@@ -116,7 +114,7 @@ def main():
             if ref is None:
                 ref = Y.clone()
             err = float((Y - ref).abs().max())
-            r = {"seg_len": seg, "mid_sort": mid_sort, "persist": persist, "block": block, "unroll": unroll, "cache": cache,
+            r = {"seg_len": seg, "mid_sort": mid_sort, "block": block, "unroll": unroll, "cache": cache,
                  "rows_per_warp": rpw, "bins": bins, "seg_order": so, "ms": ms,
                  "alg_GBps": alg / ms / 1e6, "maxdiff_vs_first": err}
             results.append(r)
