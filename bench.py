@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--exchange", type=str, default="auto", choices=["auto", "nccl", "p2p", "push"])
     p.add_argument("--tune", type=str, default="", help="comma list key=value for gae_set_tuning")
+    p.add_argument("--stages", type=int, default=1,
+                   help="N > 1 only, experimental: exchange stages pipelined with row-block SpMMs (parallel_staged.py)")
     return p.parse_args()
 
 
@@ -419,7 +421,7 @@ def run_ours(args):
     else:
         from gae_dgl_b200 import parallel
         part = parallel.build_rmat_partition(scale, total_edges, seed=1, d=D_FEAT, device=dev,
-                                             exchange=args.exchange)
+                                             exchange=args.exchange, stages=args.stages)
         fwd, bwd = part.fwd, part.bwd
         local_edges, local_rows = part.local_edges, part.local_rows
         exchange_desc = part.exchange_desc

@@ -319,7 +319,7 @@ class RmatPartition:
 
 
 def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device, exchange: str = "auto",
-                         group=None) -> RmatPartition:
+                         group=None, stages: int = 1) -> RmatPartition:
     from . import synthetic
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = 1 << scale
@@ -365,7 +365,29 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     lo = bounds[rank]
     fwd_op.X_local.copy_(synthetic.hashed_normal(hp_f.n_local, d, 2, device=device, first_row=lo))
     bwd_op.X_local.copy_(synthetic.hashed_normal(hp_b.n_local, d, 3, device=device, first_row=lo))
+    if stages > 1 and exchange in ("push", "nccl"):
+        # experimental (parallel_staged.py): B exchange stages overlapped with B row-block SpMMs
+        from .parallel_staged import StagedPartitionedSpMM
+        fwd_op = _StagedAdapter(StagedPartitionedSpMM(fwd_op, stages, group))
+        bwd_op = _StagedAdapter(StagedPartitionedSpMM(bwd_op, stages, group))
     desc = {"nccl": "pack + NCCL all-to-all-v of deduplicated halo rows, per SpMM",
             "push": "one-sided push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores), per SpMM",
             "p2p": "one-sided pull of deduplicated halo rows from peer HBM (CUDA IPC over NVLink), per SpMM"}[exchange]
+    if stages > 1:
+        desc += f"; {stages} exchange stages pipelined with row-block SpMMs"
     return RmatPartition(fwd_op, bwd_op, hp_f.n_edges, hp_f.n_local, hp_f.n_halo, desc, total_edges, d)
+
+
+class _StagedAdapter:
+    """Gives a StagedPartitionedSpMM the attribute surface RmatPartition uses (X_ext, X_local, call)."""
+
+    def __init__(self, staged):
+        self.staged = staged
+        self.X_ext = staged.base.X_ext
+
+    @property
+    def X_local(self):
+        return self.staged.base.X_local
+
+    def __call__(self):
+        return self.staged()

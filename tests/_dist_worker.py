@@ -55,6 +55,30 @@ def run(rank, world, port, scale, n_edges, d, result_dir):
             assert torch.equal(op.X_halo, Xg[plan.halo_ids])
             assert sum(plan.recv_counts) == plan.n_halo and int(plan.col.max()) < plan.n_local + plan.n_halo
             out[name] = Y
+            # staged exchange pipelined with row-block SpMM (parallel_staged): same result, and block b
+            # reads only halo rows that stages <= b have delivered (the halo is poisoned beforehand)
+            from gae_dgl_b200 import parallel_staged as PS
+            for n_stages in (1, 2, 4, 7):
+                st = PS.StagedPartitionedSpMM(op, n_stages, overlap=False)
+                sp = st.sp
+                assert sp.row_bounds[0] == 0 and sp.row_bounds[-1] == plan.n_local
+                assert sorted(torch.cat(sp.recv_pos).tolist()) == list(range(plan.n_halo))      # every halo row once
+                assert sum(int(i.numel()) for i in sp.send_idx) == int(plan.send_idx.numel())
+                edges_per_block = [int(r[-1]) for r in sp.sub_rowptr]
+                assert sum(edges_per_block) == plan.n_edges
+                op.X_halo.fill_(float("nan"))
+                op.Y.fill_(float("nan"))
+                Ys = st()
+                assert torch.equal(Ys, Y), (name, n_stages)
+                assert torch.equal(op.X_halo, Xg[plan.halo_ids])
+                # first-use tags: a halo row's stage is the block of the first local row that references it
+                deg = plan.rowptr[1:] - plan.rowptr[:-1]
+                erow = torch.repeat_interleave(torch.arange(plan.n_local), deg)
+                col64 = plan.col.to(torch.int64)
+                for h in range(0, plan.n_halo, max(1, plan.n_halo // 50)):
+                    first_row = int(erow[col64 == plan.n_local + h].min())
+                    blk = max(b for b in range(sp.n_stages) if sp.row_bounds[b] <= first_row)
+                    assert int(sp.halo_stage[h]) == blk
         # global ground truth from the full edge stream
         S, D = synthetic.rmat_edges(scale, n_edges, seed=1)
         rp, col = O.coo_to_csr(S, D, n)
