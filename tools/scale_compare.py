@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--base-edges", type=int, default=100_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--modes", type=str, default="push,nccl")
+    ap.add_argument("--stages", type=str, default="", help="comma list, e.g. 2,4,8: also time parallel_staged on each mode")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device(f"cuda:{int(os.environ['LOCAL_RANK'])}")
@@ -54,6 +55,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[mode] = {"exchange_only_ms_per_step": float(t[0]), "step_ms": float(t[1]),
                      "edges_per_s": total / (float(t[1]) * 1e-3)}
+        # staged exchange pipelined with row-block SpMMs, same partition, same buffers
+        for n_stages in [int(v) for v in args.stages.split(",") if v]:
+            if mode not in ("push", "nccl"):
+                continue
+            from gae_dgl_b200.parallel_staged import StagedPartitionedSpMM
+            ref_f, ref_b = f().clone(), b().clone()
+            sf, sb = StagedPartitionedSpMM(f, n_stages), StagedPartitionedSpMM(b, n_stages)
+            for _ in range(3):
+                sf(); sb()
+            torch.cuda.synchronize(); dist.barrier()
+            err = max(float((sf() - ref_f).abs().max()), float((sb() - ref_b).abs().max()))
+            torch.cuda.synchronize(); dist.barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(st)
+            for _ in range(args.steps):
+                sf(); sb()
+            s1.record(st)
+            s1.synchronize()
+            ts = torch.tensor([s0.elapsed_time(s1) / args.steps, err], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            out[f"{mode}_staged{n_stages}"] = {"step_ms": float(ts[0]), "edges_per_s": total / (float(ts[0]) * 1e-3),
+                                               "max_abs_diff_vs_unstaged": float(ts[1]),
+                                               "stage_rows_rank0": [int(p_.numel()) for p_ in sf.sp.recv_pos]}
+            del sf, sb
         del f, b, ops_, new
         torch.cuda.empty_cache()
     if rank == 0:
