@@ -19,7 +19,7 @@ sorted by (dst, src), duplicates kept.  adjacency_matrix() has rows = dst, cols 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, Iterable, List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 import torch

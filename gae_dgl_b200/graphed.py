@@ -9,7 +9,7 @@ replay), and Adam runs with capturable=True.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable
 
 import torch
 

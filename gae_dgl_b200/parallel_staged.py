@@ -22,10 +22,9 @@ block b only reads halo rows delivered by stages <= b (the halo is poisoned with
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, List, Optional
+from typing import List, Optional
 
 import torch
-import torch.distributed as dist
 
 from . import ops
 from ._lib import GaeError

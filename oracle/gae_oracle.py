@@ -33,7 +33,6 @@ calls.  The known-answer pins of SURVEY.md section 8c are checked in the same te
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch

@@ -12,7 +12,7 @@ import torch
 
 import gae_dgl_b200 as G
 from gae_dgl_b200 import _lib, ops, synthetic
-from gae_dgl_b200.graph import coo_to_csr_numpy, coo_to_csr_torch
+from gae_dgl_b200.graph import coo_to_csr_torch
 from oracle import gae_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

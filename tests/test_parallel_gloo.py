@@ -3,7 +3,6 @@ import os
 import socket
 
 import pytest
-import torch
 import torch.multiprocessing as mp
 
 from gae_dgl_b200 import parallel

@@ -14,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-import gae_dgl_b200 as G  # noqa: E402
 from gae_dgl_b200 import _lib, ops, synthetic  # noqa: E402
 from gae_dgl_b200.graph import coo_to_csr_torch  # noqa: E402
 
