@@ -149,7 +149,6 @@ def test_spmm_weighted_accumulate_and_unaligned(cuda):
     ops.spmm(rp, cl, X.to(cuda), out=out, accumulate=True)
     assert rel_err(out, Y0.double() + O.spmm_sum(rowptr, col, X.double())) < TOL
     # scalar fallback: leading dimension not a multiple of 4, called through the raw C ABI
-    import ctypes
     Xu = torch.zeros(n, 27, device=cuda)
     Xu[:, :24] = X.to(cuda)
     Yu = torch.zeros(n, 25, device=cuda)
@@ -581,7 +580,6 @@ def test_spmm_full_size_c4_properties(cuda):
 
 def test_c_abi_error_paths_on_device(cuda):
     """Error behaviour of the C ABI: codes, messages, no partial work on bad input."""
-    import ctypes
     lib = _lib.load()
     Z = torch.randn(64, 80, device=cuda)
     rp = torch.zeros(65, dtype=torch.int64, device=cuda)
