@@ -60,25 +60,26 @@ class GCN(nn.Module):
         self.apply_mod = NodeApplyModule(in_feats, out_feats, activation)
 
     def forward(self, g, feature):
-        g.ndata['h'] = feature
-        g.update_all(gcn_msg, gcn_reduce)
-        g.apply_nodes(func=self.apply_mod)
-        h = g.ndata.pop('h')
-        return h
+        # the node frame carries the data through both calls and is emptied of 'h' again on the way
+        # out (gae.py:30 pops it: after encode() the graph has no 'h' until the caller sets one)
+        frame = g.ndata
+        frame['h'] = feature
+        g.update_all(gcn_msg, gcn_reduce)          # K1: Y = A H
+        g.apply_nodes(func=self.apply_mod)         # K3: act(Y W^T + b)
+        return frame.pop('h')
 
 
 def _build_layers(in_dim: int, hidden_dims: Sequence[int]):
-    # gae.py:35-45: ReLU on every layer but the last; a single layer gets the identity
-    if len(hidden_dims) >= 2:
-        layers = [GCN(in_dim, hidden_dims[0], F.relu)]
-        for i in range(1, len(hidden_dims)):
-            if i != len(hidden_dims) - 1:
-                layers.append(GCN(hidden_dims[i - 1], hidden_dims[i], F.relu))
-            else:
-                layers.append(GCN(hidden_dims[i - 1], hidden_dims[i], _IDENTITY))
-    else:
-        layers = [GCN(in_dim, hidden_dims[0], _IDENTITY)]
-    return layers
+    """gae.py:35-45: ReLU on every layer but the last, identity on the last (a single layer is the last).
+
+    The reference builds `GCN(in_dim, hidden_dims[0], F.relu)` once more than it keeps (:35 is
+    overwritten by :37 or :45), which draws one extra set of first-layer initial weights from torch's
+    generator.  The same draw is made here, so `torch.manual_seed(s); GAE(...)` starts from bit-identical
+    weights in both code bases (pinned by tests/test_oracle_pins.py against the reference run)."""
+    nn.Linear(in_dim, hidden_dims[0])              # the discarded draw
+    dims = [in_dim] + list(hidden_dims)
+    last = len(hidden_dims) - 1
+    return [GCN(dims[i], dims[i + 1], _IDENTITY if i == last else F.relu) for i in range(len(hidden_dims))]
 
 
 class InnerProductDecoder(nn.Module):
@@ -142,19 +143,19 @@ class GAE(nn.Module):
         self.layers = nn.ModuleList(_build_layers(in_dim, hidden_dims))
         self.decoder = InnerProductDecoder(activation=_IDENTITY)
 
-    def forward(self, g):
-        h = g.ndata['h']
-        for conv in self.layers:
-            h = conv(g, h)
-        g.ndata['h'] = h          # gae.py:53 side effect kept: features replaced by embeddings
-        adj_rec = self.decoder(h)
-        return adj_rec
-
     def encode(self, g):
-        h = g.ndata['h']
-        for conv in self.layers:
-            h = conv(g, h)
-        return h
+        """gae.py:57-61: embeddings; the graph is left without ndata['h'] (GCN.forward pops it)."""
+        z = g.ndata['h']
+        for layer in self.layers:
+            z = layer(g, z)
+        return z
+
+    def forward(self, g):
+        """gae.py:49-55: logits [N, N]; side effect kept: the input features in ndata['h'] are replaced
+        by the embeddings (:53)."""
+        z = self.encode(g)
+        g.ndata['h'] = z
+        return self.decoder(z)
 
     def loss(self, g, pos_weight: Optional[float] = None, mask: Optional[torch.Tensor] = None,
              transductive: bool = False, per_graph: bool = False, fused_step: Optional[bool] = None):

@@ -320,3 +320,21 @@ def test_pos_weight_matches_the_reference_expressions_bit_for_bit():
         adj_sum = torch.tensor(float(e), dtype=torch.float32)          # == adj.sum() of a 0/1(/2..) fp32 matrix
         assert G.pos_weight_of(g) == float((n * n - adj_sum) / adj_sum)
         assert G.pos_weight_of(g, transductive=True) == float(torch.Tensor([float(n * n - adj_sum) / adj_sum])[0])
+
+
+def test_mol_dataset_surface():
+    """gae_dgl/dataset.py:3-12 surface (len, integer indexing, .graphs) + the additions, and it feeds a
+    DataLoader with a collate_fn exactly as train_inductive.py:84 does."""
+    from torch.utils.data import DataLoader
+    graphs = synthetic.zinc_like_dataset(10, seed=3)
+    ds = G.MolDataset(graphs)
+    assert len(ds) == 10 and ds[3] is graphs[3] and ds.graphs[7] is graphs[7]
+    assert ds[2:4] == graphs[2:4] and ds[np.array([1, 5])] == [graphs[1], graphs[5]]
+    assert ds.num_nodes.tolist() == [g.number_of_nodes() for g in graphs]
+    assert ds.num_edges.tolist() == [g.number_of_edges() for g in graphs]
+    assert [g for g in ds] == graphs
+    seen = []
+    for batch in DataLoader(ds, batch_size=4, shuffle=False, collate_fn=lambda samples: samples):
+        assert all(isinstance(g, G.DGLGraph) for g in batch)
+        seen += batch
+    assert seen == graphs

@@ -228,3 +228,60 @@ def test_oracle_matches_reference_run_forward_and_steps(tag, dtype):
     with torch.no_grad():
         ev = O.bce_loss(model(rowptr, col, c.X, c.mask_eval), c.adj, pw)
     assert abs(float(ev) - c.loss_eval) < 5e-5 * abs(c.loss_eval)
+
+
+@pytest.mark.parametrize("tag", RF.CASES)
+def test_module_init_is_bit_identical_to_the_reference_run(tag):
+    """`torch.manual_seed(s); GAE(in_dim, hidden)` draws the same initial weights as the reference's
+    constructor did in the fixture run (including the first-layer set the reference draws and discards,
+    gae.py:35 vs :37/:45)."""
+    import gae_dgl_b200 as G
+    c = RF.load_case(tag)
+    seed = {"A": 1, "B": 2, "C": 3, "D": 4}[tag]              # make_golden_reference.py: run_case(..., seed=)
+    torch.manual_seed(seed)
+    model = G.GAE(c.in_dim, c.hidden)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(c.init.keys())
+    for k, ref in c.init.items():
+        assert torch.equal(sd[k], ref), (tag, k)
+
+
+@pytest.mark.parametrize("tag", RF.CASES)
+def test_module_glue_matches_reference_run_with_cpu_test_doubles(tag, monkeypatch):
+    """The Python glue of gae.py (frame handling, layer order, activations, the 'h' write-back and pop)
+    executed on CPU with test doubles in place of the three CUDA ops, against the reference run."""
+    import gae_dgl_b200 as G
+    from gae_dgl_b200 import ops
+    c = RF.load_case(tag)
+    members = []
+    for s, d, n, X in c.members:
+        g = G.DGLGraph()
+        g.add_nodes(n)
+        g.add_edges(s.tolist(), d.tolist())
+        g.ndata["h"] = X.clone()
+        members.append(g)
+    bg = G.batch(members) if len(members) > 1 else members[0]
+
+    def spmm_double(x, graph):
+        return O.spmm_sum(graph.csr().rowptr, graph.csr().col, x)
+
+    def linear_double(y, W, b, act):
+        out = F.linear(y, W, b)
+        return F.relu(out) if act == ops.ACT_RELU else out
+
+    def logits_double(z, p, mask, rng_state):
+        return O.decoder_logits(z, c.masks[0] if mask is None else mask, p)
+
+    monkeypatch.setattr(ops.SpMMFunction, "apply", staticmethod(spmm_double))
+    monkeypatch.setattr(ops.LinearActFunction, "apply", staticmethod(linear_double))
+    monkeypatch.setattr(ops.DecoderLogitsFunction, "apply", staticmethod(logits_double))
+    model = G.GAE(c.in_dim, c.hidden)
+    model.load_state_dict(c.init)
+    with torch.no_grad():
+        z = model.encode(bg)
+        assert "h" not in bg.ndata                      # gae.py:30 pop, no write-back in encode (:57-61)
+        assert _rel(z, c.encode) < 1e-5
+        bg.ndata["h"] = c.X.clone()
+        logits = model.forward(bg)
+        assert _rel(logits, c.logits) < 1e-5
+        assert _rel(bg.ndata["h"], c.emb) < 1e-5        # gae.py:53 write-back
