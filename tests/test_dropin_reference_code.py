@@ -119,3 +119,102 @@ def test_reference_transductive_invariants_over_the_drop_in_graph():
     assert ns["pos_weight"].shape == (1,)
     assert G.pos_weight_of(g, transductive=True) == float(ns["pos_weight"][0])
     assert G.pos_weight_of(g) == c.pos_weight
+
+
+# ---- prepare_data.py:26-69 (atom features, mols2graphs) over duck-typed molecules ----------------
+
+class _Atom:
+    def __init__(self, idx, symbol, degree, charge=0, chiral=0, aromatic=False):
+        self.idx, self.symbol, self.degree, self.charge, self.chiral, self.aromatic = idx, symbol, degree, charge, chiral, aromatic
+
+    def GetIdx(self): return self.idx                      # noqa: E704
+    def GetSymbol(self): return self.symbol                # noqa: E704
+    def GetDegree(self): return self.degree                # noqa: E704
+    def GetFormalCharge(self): return self.charge          # noqa: E704
+    def GetChiralTag(self): return self.chiral             # noqa: E704
+    def GetIsAromatic(self): return self.aromatic          # noqa: E704
+
+
+class _Bond:
+    def __init__(self, a, b): self.a, self.b = a, b        # noqa: E704
+    def GetBeginAtom(self): return self.a                  # noqa: E704
+    def GetEndAtom(self): return self.b                    # noqa: E704
+
+
+class _Mol:
+    """Stands in for an RDKit Mol (RDKit is not installed): symbols + bond list."""
+
+    def __init__(self, symbols, bonds, aromatic=()):
+        deg = [0] * len(symbols)
+        for u, v in bonds:
+            deg[u] += 1
+            deg[v] += 1
+        self.atoms = [_Atom(i, s, deg[i], aromatic=i in aromatic) for i, s in enumerate(symbols)]
+        self.bonds = [_Bond(self.atoms[u], self.atoms[v]) for u, v in bonds]
+
+    def GetNumAtoms(self): return len(self.atoms)          # noqa: E704
+    def GetAtoms(self): return self.atoms                  # noqa: E704
+    def GetBonds(self): return self.bonds                  # noqa: E704
+
+
+def _reference_graph_builder():
+    with open(os.path.join(REF, "prepare_data.py")) as f:
+        tree = ast.parse(f.read())
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.FunctionDef) and n.name in ("onek_encoding_unk", "atom_features", "mols2graphs"))
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") in ("ELEM_LIST", "ATOM_FDIM"))]
+    ns = {"torch": torch, "tqdm": lambda it: it, "DGLGraph": G.DGLGraph}      # prepare_data.py:8,11-12
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "prepare_data.py:14-69", "exec"), ns)
+    return ns
+
+
+def test_reference_graph_builder_over_the_drop_in_graph(tmp_path):
+    """prepare_data.py's own mols2graphs builds gae_dgl_b200.DGLGraph objects; they survive the dill
+    round trip of :102-103 / train_inductive.py:76-77, batch block-diagonally and carry the 39-d atom
+    features the synthetic ZINC-shaped generator imitates."""
+    import dill
+    ns = _reference_graph_builder()
+    assert ns["ATOM_FDIM"] == 39
+    mols = [_Mol(["C", "C", "O"], [(0, 1), (1, 2)]),                                     # ethanol
+            _Mol(["C"] * 6, [(i, (i + 1) % 6) for i in range(6)], aromatic=range(6)),    # benzene ring
+            _Mol(["N", "C", "Xx"], [(0, 1), (1, 2)])]                                    # unknown element -> last slot
+    graphs = ns["mols2graphs"](mols)
+    assert all(isinstance(g, G.DGLGraph) for g in graphs)
+    assert [g.number_of_nodes() for g in graphs] == [3, 6, 3] and [g.number_of_edges() for g in graphs] == [4, 12, 4]
+    for g in graphs:
+        h = g.ndata["h"]
+        assert h.shape == (g.number_of_nodes(), 39) and h.dtype == torch.float32
+        assert torch.equal(h[:, :23].sum(1), torch.ones(len(h))) and torch.equal(h[:, 23:29].sum(1), torch.ones(len(h)))
+        A = g.adjacency_matrix().to_dense()
+        assert torch.equal(A, A.t())                                  # both directions added (:61-64)
+    assert graphs[2].ndata["h"][2, 22] == 1.0                         # 'unknown'
+    assert bool(graphs[1].ndata["h"][:, 38].all()) and not bool(graphs[0].ndata["h"][:, 38].any())
+    path = tmp_path / "graphs.pkl"
+    with open(path, "wb") as f:
+        dill.dump(graphs, f)                                          # prepare_data.py:102-103
+    with open(path, "rb") as f:
+        loaded = dill.load(f)                                         # train_inductive.py:76-77
+    bg = G.batch(loaded)
+    assert bg.number_of_nodes() == 12 and bg.number_of_edges() == 20 and bg.batch_num_nodes == [3, 6, 3]
+    A = bg.adjacency_matrix().to_dense()
+    assert float(A[:3, 3:].abs().sum()) == 0.0 and float(A[3:9, 9:].abs().sum()) == 0.0     # block diagonal
+    assert torch.equal(bg.ndata["h"], torch.cat([g.ndata["h"] for g in graphs]))
+    # the synthetic generator uses the same 39-column layout
+    from gae_dgl_b200.synthetic import zinc_like_dataset
+    hs = torch.cat([g.ndata["h"] for g in zinc_like_dataset(20, seed=0)])
+    for lo, hi in ((0, 23), (23, 29), (29, 34), (34, 38)):
+        assert torch.equal(hs[:, lo:hi].sum(1), torch.ones(len(hs)))
+
+
+def test_reference_collate_over_the_drop_in_package():
+    """train_inductive.py:31-35 `collate` with this package's graph module standing in for `dgl`."""
+    with open(os.path.join(REF, "train_inductive.py")) as f:
+        tree = ast.parse(f.read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "collate"]
+    from gae_dgl_b200 import graph as dgl_standin
+    ns = {"torch": torch, "dgl": dgl_standin, "device": torch.device("cpu")}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "train_inductive.py::collate", "exec"), ns)
+    c = RF.load_case("B")
+    bg = ns["collate"](_members(c))
+    assert bg.number_of_nodes() == c.n and torch.equal(bg.adjacency_matrix().to_dense(), c.adj)
+    assert torch.equal(bg.ndata["h"], c.X)
