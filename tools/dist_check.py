@@ -21,8 +21,9 @@ def main():
     scale, n_edges, d = 16, 2_000_000, 64
     n = 1 << scale
     ok = True
-    for exchange in ("nccl", "p2p", "push"):
-        part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange)
+    # (exchange, stages): stages > 1 = parallel_staged (exchange pipelined with row-block SpMMs)
+    for exchange, stages in (("nccl", 1), ("p2p", 1), ("push", 1), ("push", 4), ("nccl", 3)):
+        part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange, stages=stages)
         Yf = part.fwd().clone()
         Yb = part.bwd().clone()
         torch.cuda.synchronize()
@@ -37,7 +38,7 @@ def main():
         ref_b = torch.from_numpy(c_spmm.spmm_f64acc(rpt.numpy(), colt.numpy(), dY))[lo:hi]
         ef = float((Yf.double().cpu() - ref_f).abs().max() / max(float(ref_f.abs().max()), 1.0))
         eb = float((Yb.double().cpu() - ref_b).abs().max() / max(float(ref_b.abs().max()), 1.0))
-        print(f"[rank {rank}] exchange={exchange} fwd_err={ef:.2e} bwd_err={eb:.2e} halo={part.halo_rows} "
+        print(f"[rank {rank}] exchange={exchange} stages={stages} fwd_err={ef:.2e} bwd_err={eb:.2e} halo={part.halo_rows} "
               f"local_rows={part.local_rows} local_edges={part.local_edges}", flush=True)
         ok = ok and ef < 1e-5 and eb < 1e-5
         del part
