@@ -12,11 +12,11 @@ static std::atomic<int64_t> g_launches{0};
 // defaults (B200 sweeps, profiles/r01_sweep_*.json): register-gather variant, 4 gathers in flight per
 // lane at 40 registers (48 warps/SM), 64-thread CTAs, plain caching, warp per row; decoder dense pass with
 // both GEMMs on the tensor cores (dec_mma = 1)
-static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {4}, {64}, {0}, {1}, {0}, {2}, {1}, {2}, {1}, {1}};
+static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {4}, {64}, {0}, {1}, {0}, {2}, {1}, {2}, {1}, {0}, {1}};
 static const char *const g_tuning_names[T_COUNT] = {"spmm_variant", "spmm_unroll", "spmm_block",
                                                      "spmm_cache", "spmm_rows_per_warp", "dec_splits",
                                                      "spmm_stages", "spmm_bins", "dec_rows",
-                                                     "spmm_seg_order", "dec_mma"};
+                                                     "spmm_seg_order", "spmm_fused", "dec_mma"};
 
 void set_error(const char *fmt, ...) {
     va_list ap;

@@ -299,6 +299,9 @@ static cudaError_t launch_vec(const SpmmArgs &a, int rows_per_warp, int unroll, 
 }
 
 cudaError_t spmm_stream_launch(const StreamArgs &a, int d, bool seg, int stages, int mode, cudaStream_t st);
+bool spmm_fused_launch(const int64_t *rowptr, const int32_t *col, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                       int32_t d, const gae_hub_plan_t *plan, float *partial_ws, int64_t ldp, bool seg_order,
+                       cudaStream_t st, cudaError_t *err);
 
 }  // namespace gae
 
@@ -364,6 +367,21 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     }
     const bool binned = plan && plan->mid_rows && plan->short_rows && plan->empty_rows && d % 4 == 0 && d <= 64 &&
                         plan->short_max == 4 && !vals && tuning(T_SPMM_BINS) != 0;
+    if (binned && !accumulate && cache == 0 && tuning(T_SPMM_FUSED) != 0) {
+        // experimental: all row classes and the hub segments in one launch (spmm_fused.cu)
+        const int64_t ldp = (int64_t)((d + 3) / 4) * 4;
+        cudaError_t e = cudaSuccess;
+        if (spmm_fused_launch(rowptr, col, X, ldx, Y, ldy, d, plan, partial_ws, ldp, tuning(T_SPMM_SEG_ORDER) != 0, st, &e)) {
+            GAE_CUDA(e);
+            if (use_plan) {
+                const int64_t threads = plan->n_long * ((d + 3) / 4);
+                spmm_hub_reduce_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(
+                    partial_ws, ldp, plan->long_row, plan->long_seg_ptr, plan->n_long, Y, ldy, d, 0);
+                GAE_LAUNCH_CHECK();
+            }
+            return GAE_OK;
+        }
+    }
     if (binned) {
         // degree-binned row pass: zero fill | short rows 4 per warp | a warp per remaining row
         if (plan->n_empty > 0 && !accumulate) {

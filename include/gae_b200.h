@@ -44,7 +44,8 @@ const char *gae_version(void);
 const char *gae_last_error_string(void);
 /* Tuning knobs used by bench sweeps.  Keys (default): "spmm_variant" (0: register gather; 1 / 2:
  * streaming cp.async.bulk / LDGSTS), "spmm_unroll" (4), "spmm_block" (64), "spmm_cache" (0),
- * "spmm_rows_per_warp" (1), "spmm_stages" (2), "spmm_bins" (1), "spmm_seg_order" (1),
+ * "spmm_rows_per_warp" (1), "spmm_stages" (2), "spmm_bins" (1), "spmm_seg_order" (1), "spmm_fused"
+ * (0; experimental single-launch form of the binned forward, not measured yet),
  * "dec_splits" (0 = auto), "dec_rows" (2), "dec_mma" (1: decoder dense pass on the tensor cores for
  * d <= 16; 0: SIMT).  Results are independent of every knob up to fp32 summation order.
  * Unknown keys return GAE_ERR_INVALID_ARG.  gae_get_tuning returns the value or -1. */

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--out", type=str, default="")
     ap.add_argument("--mid-sort", type=str, default="0", help="0 / 1: degree-sorted mid-row list")
     ap.add_argument("--seg-orders", type=str, default="0,1")
+    ap.add_argument("--fused", type=str, default="0", help="spmm_fused values (experimental one-launch forward)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n = 1 << args.scale
@@ -100,9 +101,10 @@ def main():
         _lib.set_tuning("spmm_variant", 0)
         if "0" not in args.variants.split(","):
             continue
-        for block, unroll, cache, rpw, bins, so in itertools.product(
+        for block, unroll, cache, rpw, bins, so, fused in itertools.product(
                 blocks, unrolls, caches, (1,), [int(b) for b in args.bins.split(",")],
-                [int(v) for v in args.seg_orders.split(",")]):
+                [int(v) for v in args.seg_orders.split(",")], [int(v) for v in args.fused.split(",")]):
+            _lib.set_tuning("spmm_fused", fused)
             _lib.set_tuning("spmm_bins", bins)
             _lib.set_tuning("spmm_seg_order", so)
             _lib.set_tuning("spmm_block", block)
@@ -113,7 +115,7 @@ def main():
             if ref is None:
                 ref = Y.clone()
             err = float((Y - ref).abs().max())
-            r = {"seg_len": seg, "mid_sort": mid_sort, "block": block, "unroll": unroll, "cache": cache,
+            r = {"seg_len": seg, "mid_sort": mid_sort, "fused": fused, "block": block, "unroll": unroll, "cache": cache,
                  "rows_per_warp": rpw, "bins": bins, "seg_order": so, "ms": ms,
                  "alg_GBps": alg / ms / 1e6, "maxdiff_vs_first": err}
             results.append(r)
