@@ -104,6 +104,8 @@ SIGNATURES = {
     "gae_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8 * 64), POINTER(c_int64)]),
     "gae_ipc_open_handle": (c_int, [POINTER(c_uint8 * 64), POINTER(c_void_p)]),
     "gae_ipc_close_handle": (c_int, [c_void_p]),
+    "gae_adam_step_f32": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_int64), c_float, c_float, c_float, c_float, c_int64, c_void_p]),
 }
 
 _lib = None

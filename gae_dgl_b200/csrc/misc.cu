@@ -1,4 +1,5 @@
 // K4 dropout, graph-indexing helpers, halo pack / one-sided pull, CUDA IPC plumbing.
+#include <math.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -183,9 +184,63 @@ __global__ void push_rows_p2p_kernel(const float *__restrict__ X, int64_t ldx, c
     *dst = v;
 }
 
+// torch.optim.Adam step (train_inductive.py:40,52; no weight decay, no amsgrad) over up to
+// GAE_ADAM_MAX_TENSORS parameter tensors in ONE launch.  Same update as torch's:
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+struct AdamArgs {
+    float *p[GAE_ADAM_MAX_TENSORS];
+    const float *g[GAE_ADAM_MAX_TENSORS];
+    float *m[GAE_ADAM_MAX_TENSORS];
+    float *v[GAE_ADAM_MAX_TENSORS];
+    int64_t end[GAE_ADAM_MAX_TENSORS];   // exclusive prefix ends of the flattened element range
+    int32_t n_tensors;
+    float b1, b2, eps, step_size, inv_bias2_sqrt;
+};
+
+__global__ void adam_step_kernel(const AdamArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.end[a.n_tensors - 1]) return;
+    int t = 0;
+    while (i >= a.end[t]) ++t;
+    const int64_t k = i - (t ? a.end[t - 1] : 0);
+    const float g = a.g[t][k];
+    const float m = fmaf(a.b1, a.m[t][k] - g, g);                 // lerp: g + b1 (m - g) == b1 m + (1-b1) g
+    const float v = fmaf(a.b2, a.v[t][k], (1.f - a.b2) * g * g);
+    a.m[t][k] = m;
+    a.v[t][k] = v;
+    const float denom = sqrtf(v) * a.inv_bias2_sqrt + a.eps;
+    a.p[t][k] -= a.step_size * (m / denom);
+}
+
 }  // namespace gae
 
 using namespace gae;
+
+extern "C" int gae_adam_step_f32(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
+                                 float *const *exp_avg_sq, const int64_t *numel, float lr, float beta1, float beta2,
+                                 float eps, int64_t step, void *stream) {
+    GAE_CHECK_ARG(n_tensors >= 1 && n_tensors <= GAE_ADAM_MAX_TENSORS, "1 <= n_tensors <= GAE_ADAM_MAX_TENSORS");
+    GAE_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel, "null pointer");
+    GAE_CHECK_ARG(step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+                  "bad hyper-parameters (step counts from 1)");
+    AdamArgs a{};
+    int64_t total = 0;
+    for (int t = 0; t < n_tensors; ++t) {
+        GAE_CHECK_ARG(params[t] && grads[t] && exp_avg[t] && exp_avg_sq[t] && numel[t] > 0, "null / empty tensor");
+        a.p[t] = params[t]; a.g[t] = grads[t]; a.m[t] = exp_avg[t]; a.v[t] = exp_avg_sq[t];
+        total += numel[t];
+        a.end[t] = total;
+    }
+    a.n_tensors = n_tensors;
+    a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+    // bias corrections in double on the host, as torch computes them from the python step count
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.step_size = (float)((double)lr / bc1);
+    a.inv_bias2_sqrt = (float)(1.0 / sqrt(bc2));
+    adam_step_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    GAE_LAUNCH_CHECK();
+    return GAE_OK;
+}
 
 extern "C" int gae_dropout_fwd_f32(const float *Z, int64_t ldz, float *Zd, int64_t ldzd, uint8_t *mask,
                                    int64_t n, int32_t d, float p, uint64_t seed, uint64_t offset,

@@ -44,6 +44,8 @@ def build_parser():
     parser.add_argument('--resume', type=str, default=None, help='checkpoint (ep{NN}.pkl or .ckpt) to resume from')
     parser.add_argument('--per_graph_decoder', action='store_true',
                         help='decode each molecule separately (block-diagonal pairs) instead of the full batch matrix')
+    parser.add_argument('--native_step', action='store_true',
+                        help='experimental: train steps without autograd / torch.optim dispatch (native_step.py)')
     parser.add_argument('--host_collate', action='store_true',
                         help='collate each batch from the member graphs on the host (reference flow) instead of the '
                              'device-resident packed dataset')
@@ -63,7 +65,15 @@ class Trainer:
         self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr, fused=self.device.type == 'cuda')
         self.dense = bool(getattr(args, 'dense_decoder', False))
         self.per_graph = bool(getattr(args, 'per_graph_decoder', False))
+        self.native = None
+        self._want_native = bool(getattr(args, 'native_step', False)) and isinstance(model, GAE) and not self.dense
+        self._make_native()
         print('Total Parameters:', sum([p.nelement() for p in self.model.parameters()]))
+
+    def _make_native(self):
+        if self._want_native:
+            from .native_step import NativeTrainStep
+            self.native = NativeTrainStep(self.model, self.optim)
 
     def loss(self, g):
         if not self.dense:
@@ -77,6 +87,9 @@ class Trainer:
         """One step (train_inductive.py:43-53).  sync=True returns loss.item() like the reference
         (a device->host sync per step); sync=False returns the 0-dim device tensor so the caller can
         keep the GPU queue full and read the losses once per epoch."""
+        if train and self.native is not None:    # loss + backward + Adam as two native calls
+            loss = self.native(g, per_graph=self.per_graph)
+            return loss.item() if sync else loss
         with torch.set_grad_enabled(train):      # validation needs no gradient work
             loss = self.loss(g)
         if train:
@@ -88,6 +101,8 @@ class Trainer:
     def save(self, epoch, save_dir):
         output_path = os.path.join(save_dir, 'ep{:02}.pkl'.format(epoch))
         torch.save(self.model.state_dict(), output_path)     # reference format (train_inductive.py:55-57)
+        if self.native is not None:
+            self.native.sync_state()
         torch.save({'epoch': epoch, 'model': self.model.state_dict(), 'optim': self.optim.state_dict()},
                    os.path.join(save_dir, 'ep{:02}.ckpt'.format(epoch)))
         return output_path
@@ -98,6 +113,7 @@ class Trainer:
         if isinstance(st, dict) and 'model' in st and 'optim' in st:
             self.model.load_state_dict(st['model'])
             self.optim.load_state_dict(st['optim'])
+            self._make_native()                  # the optimiser state tensors were replaced
             return int(st.get('epoch', -1)) + 1
         self.model.load_state_dict(st)
         return 0

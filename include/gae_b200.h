@@ -258,6 +258,16 @@ int gae_ipc_get_handle(const void *dev_ptr, uint8_t handle_out[64], int64_t *off
 int gae_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out);
 int gae_ipc_close_handle(void *dev_ptr);
 
+/* ---- optimiser step (train_inductive.py:40,52: torch.optim.Adam, no weight decay / amsgrad) ---- */
+/* One launch over up to GAE_ADAM_MAX_TENSORS parameter tensors (device pointers passed in HOST arrays):
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * `step` counts from 1.  exp_avg / exp_avg_sq are the state tensors torch.optim.Adam keeps under the same
+ * names, so optimiser checkpoints stay interchangeable. */
+#define GAE_ADAM_MAX_TENSORS 16
+int gae_adam_step_f32(int32_t n_tensors, float *const *params, const float *const *grads,
+                      float *const *exp_avg, float *const *exp_avg_sq, const int64_t *numel, float lr,
+                      float beta1, float beta2, float eps, int64_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

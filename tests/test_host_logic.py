@@ -338,3 +338,26 @@ def test_mol_dataset_surface():
         assert all(isinstance(g, G.DGLGraph) for g in batch)
         seen += batch
     assert seen == graphs
+
+
+def test_native_adam_formula_matches_torch_optim():
+    """The update gae_adam_step_f32 implements (csrc/misc.cu: lerp form of m, bias corrections from the
+    step count in double, p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)) tracks torch.optim.Adam."""
+    torch.manual_seed(0)
+    p_ref = torch.randn(50, 7, requires_grad=True)
+    opt = torch.optim.Adam([p_ref], lr=1e-2)
+    p = p_ref.detach().clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    b1, b2, eps, lr = 0.9, 0.999, 1e-8, 1e-2
+    for step in range(1, 8):
+        g = torch.randn(50, 7)
+        p_ref.grad = g.clone()
+        opt.step()
+        m = g + b1 * (m - g)
+        v = b2 * v + (1.0 - b2) * g * g
+        step_size = np.float32(lr / (1.0 - b1 ** step))
+        inv_bc2 = np.float32(1.0 / np.sqrt(1.0 - b2 ** step))
+        p = p - float(step_size) * (m / (v.sqrt() * float(inv_bc2) + eps))
+        assert float((p - p_ref.detach()).abs().max()) < 2e-6 * max(1.0, float(p_ref.abs().max())), step
+    st = opt.state[p_ref]
+    assert float((m - st["exp_avg"]).abs().max()) < 1e-6 and float((v - st["exp_avg_sq"]).abs().max()) < 1e-6
