@@ -50,10 +50,11 @@ def parse_args():
     p.add_argument("--no-pubmed", action="store_true")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--exchange", type=str, default="auto", choices=["auto", "nccl", "p2p", "push"])
+    p.add_argument("--exchange", type=str, default="auto", choices=["auto", "halo", "nccl", "p2p", "push"])
     p.add_argument("--tune", type=str, default="", help="comma list key=value for gae_set_tuning")
-    p.add_argument("--stages", type=int, default=1,
-                   help="N > 1 only, experimental: exchange stages pipelined with row-block SpMMs (parallel_staged.py)")
+    p.add_argument("--stages", type=int, default=8,
+                   help="N > 1, exchange 'halo': stages of the one-sided push overlapped with that many row-block SpMMs")
+    p.add_argument("--push-ctas", type=int, default=0, help="N > 1, exchange 'halo': CTAs of the push kernel (0 = 64)")
     return p.parse_args()
 
 
@@ -421,7 +422,7 @@ def run_ours(args):
     else:
         from gae_dgl_b200 import parallel
         part = parallel.build_rmat_partition(scale, total_edges, seed=1, d=D_FEAT, device=dev,
-                                             exchange=args.exchange, stages=args.stages)
+                                             exchange=args.exchange, stages=args.stages, push_ctas=args.push_ctas)
         fwd, bwd = part.fwd, part.bwd
         local_edges, local_rows = part.local_edges, part.local_rows
         exchange_desc = part.exchange_desc

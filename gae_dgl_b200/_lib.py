@@ -51,6 +51,26 @@ class StepDesc(Structure):
     ]
 
 
+class HaloExchangeStruct(Structure):
+    """Mirror of gae_halo_exchange_t."""
+    _fields_ = [
+        ("world", c_int32), ("rank", c_int32), ("n_stages", c_int32), ("d", c_int32),
+        ("ld", c_int64),
+        ("x_local", c_void_p), ("peer_x", c_void_p), ("peer_flags", c_void_p), ("flags", c_void_p),
+        ("send_src", c_void_p), ("send_peer", c_void_p), ("send_dst", c_void_p),
+        ("stage_ptr", c_void_p), ("stage_done", c_void_p),
+        ("push_ctas", c_int32), ("push_threads", c_int32), ("timeout_ms", c_int32),
+    ]
+
+
+class HaloBlockStruct(Structure):
+    """Mirror of gae_halo_block_t."""
+    _fields_ = [
+        ("row0", c_int64), ("n_rows", c_int64),
+        ("rowptr", c_void_p), ("col", c_void_p), ("plan", c_void_p), ("partial_ws", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gae_b200.h declares
 SIGNATURES = {
     "gae_version": (c_char_p, []),
@@ -104,6 +124,17 @@ SIGNATURES = {
     "gae_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8 * 64), POINTER(c_int64)]),
     "gae_ipc_open_handle": (c_int, [POINTER(c_uint8 * 64), POINTER(c_void_p)]),
     "gae_ipc_close_handle": (c_int, [c_void_p]),
+    "gae_halo_push_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
+    "gae_halo_wait_f32": (c_int, [POINTER(HaloExchangeStruct), c_int32, c_uint64, c_void_p]),
+    "gae_halo_release_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
+    "gae_halo_spmm_f32": (c_int, [POINTER(HaloExchangeStruct), POINTER(HaloBlockStruct), c_void_p, c_int64, c_uint64,
+                                  c_void_p, c_void_p]),
+    "gae_halo_status": (c_int, [POINTER(HaloExchangeStruct), POINTER(c_int64)]),
+    "gae_halo_plan_count_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, POINTER(c_int64), c_void_p]),
+    "gae_halo_plan_fill_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "gae_halo_stage_tags_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "gae_halo_push_lists_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "gae_adam_step_f32": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_int64), c_float, c_float, c_float, c_float, c_int64, c_void_p]),
 }

@@ -3,14 +3,21 @@
 Rank r owns the contiguous block of destination rows [r*V/P, (r+1)*V/P), their in-edge CSR and
 the feature rows of those vertices.  Column ids are remapped to [local | halo]: halo = sorted
 unique remote sources, which (blocks being contiguous) are already grouped by owner.  One
-exchange per SpMM moves each needed remote row exactly once:
+exchange per SpMM moves each needed remote row exactly once.  Mechanisms:
 
+  halo : (default) `HaloSpMM` -- the whole operator behind ONE C call (gae_halo_spmm_f32,
+         csrc/halo.cu): a persistent one-sided push kernel delivers the halo rows stage by stage
+         into the peers' buffers (CUDA IPC, posted NVLink stores) and publishes device-side flags;
+         the row-block SpMM of stage s starts when its flags have landed, so the transfer of the
+         later stages overlaps the aggregation of the earlier ones.  No collective, no host sync.
   nccl : pack (gae_gather_rows_f32) -> all-to-all-v (NCCL grouped send/recv over NVLink)
-         -> rows land directly in the halo region of the [local | halo] feature buffer
-  p2p  : one-sided pull -- every rank maps its peers' feature buffers through CUDA IPC and
-         gathers the rows it needs straight out of peer HBM over NVSwitch
-         (gae_pull_rows_p2p_f32): no pack, no staging copy, no sender-side kernel.
+         -> rows land directly in the halo region; then one SpMM.  Fallback when IPC is unavailable.
+  push / p2p : the round-1 one-sided push / pull bracketed by two stream-ordered NCCL barriers,
+         kept for comparison (bench.py --exchange push).
 
+Planning (halo ids, [local | halo] column remap, first-use stage tags, interleaved send lists) is
+done by the host helpers of the C ABI (gae_halo_*_host); torch.distributed only carries the
+request lists between the ranks at set-up time.
 The backward SpMM (dX = A^T dY) uses the same machinery on CSR(A^T), partitioned by source.
 Graph generation is distributed as well: every rank draws 1/P of the R-MAT edge stream and
 routes each edge to the owner of its row.
@@ -20,15 +27,19 @@ them so the planning / exchange logic runs without a GPU (the product path has n
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional
+from typing import Callable, Dict, List, Optional
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import ops
-from ._lib import GaeError
+from . import _lib, ops
+from ._lib import GaeError, HaloBlockStruct, HaloExchangeStruct
 from .graph import coo_to_csr_torch
+
+DEFAULT_STAGES = 8
 
 
 def block_bounds(n: int, world: int) -> List[int]:
@@ -67,6 +78,28 @@ class HaloPlan:
         return o.to(torch.int32)
 
 
+def _np_ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def halo_plan_host(src_global: np.ndarray, bounds: List[int], rank: int):
+    """gae_halo_plan_count_host / _fill_host on host arrays: (halo_ids int64 [H] ascending,
+    col_local int32 [E] in [local | halo], recv_counts [world])."""
+    lib = _lib.load()
+    world = len(bounds) - 1
+    src_global = np.ascontiguousarray(src_global, dtype=np.int64)
+    b = np.asarray(bounds, dtype=np.int64)
+    n_halo = ctypes.c_int64(0)
+    recv = np.zeros(world, dtype=np.int64)
+    _lib.check(lib.gae_halo_plan_count_host(_np_ptr(src_global), src_global.size, _np_ptr(b), world, rank,
+                                            ctypes.byref(n_halo), _np_ptr(recv)), "gae_halo_plan_count_host")
+    halo_ids = np.zeros(max(n_halo.value, 1), dtype=np.int64)
+    col_local = np.zeros(max(src_global.size, 1), dtype=np.int32)
+    _lib.check(lib.gae_halo_plan_fill_host(_np_ptr(src_global), src_global.size, _np_ptr(b), world, rank,
+                                           _np_ptr(halo_ids), _np_ptr(col_local)), "gae_halo_plan_fill_host")
+    return halo_ids[:n_halo.value], col_local[:src_global.size], recv.tolist()
+
+
 def build_halo_plan(src: torch.Tensor, dst: torch.Tensor, n_global: int, rank: int, world: int,
                     group=None, seg_len: int = ops.DEFAULT_SEG_LEN) -> HaloPlan:
     """`src`, `dst`: global int64 endpoints of the edges whose dst this rank owns."""
@@ -76,14 +109,13 @@ def build_halo_plan(src: torch.Tensor, dst: torch.Tensor, n_global: int, rank: i
     n_local = hi - lo
     if dst.numel() and (int(dst.min()) < lo or int(dst.max()) >= hi):
         raise GaeError("build_halo_plan: an edge's dst is not owned by this rank")
-    remote = (src < lo) | (src >= hi)
-    halo_ids = torch.unique(src[remote])                      # sorted ascending == grouped by owner
+    halo_np, col_np, recv_counts = halo_plan_host(src.cpu().numpy(), bounds, rank)
+    halo_ids = torch.from_numpy(halo_np).to(dev)
     n_halo = int(halo_ids.numel())
-    col = torch.where(remote, n_local + torch.searchsorted(halo_ids, src), src - lo)
+    col = torch.from_numpy(col_np).to(dev).to(torch.int64)
     rowptr, col32 = coo_to_csr_torch(col, dst - lo, n_local, n_cols=n_local + n_halo)
+    del col
     b = torch.tensor(bounds, device=dev, dtype=torch.int64)
-    cuts = torch.searchsorted(halo_ids, b)                    # halo range owned by each peer
-    recv_counts = (cuts[1:] - cuts[:-1]).tolist()
     # tell every owner which of its rows we need
     rc = torch.tensor(recv_counts, dtype=torch.int64, device=dev)
     sc = torch.empty_like(rc)
@@ -99,6 +131,240 @@ def build_halo_plan(src: torch.Tensor, dst: torch.Tensor, n_global: int, rank: i
         ops.order_segments_by_source(plan, rowptr, col32)
     return HaloPlan(rank, world, bounds, n_local, n_halo, halo_ids, recv_counts, send_counts, send_idx, rowptr,
                     col32, plan, int(src.numel()))
+
+
+# ------------------------------------------------------------------------------------------------
+# staged exchange plan (first-use tags, row blocks, interleaved send lists)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class StagePlan:
+    n_stages: int
+    row_bounds: List[int]                 # local row blocks, balanced by edge count; len = n_stages + 1
+    sub_rowptr: List[torch.Tensor]        # per block: rowptr rebased to 0
+    sub_col: List[torch.Tensor]           # per block: view into the local CSR's col array
+    sub_plan: List[Optional[ops.HubPlan]]
+    halo_stage: torch.Tensor              # int32 [n_halo] (host): first block that reads each halo row
+    send_stage: torch.Tensor              # int32 [S] (host): stage of every entry of HaloPlan.send_idx
+    push_src: torch.Tensor                # int64 [S]: local rows to send, sorted by stage, peers interleaved
+    push_peer: torch.Tensor               # int32 [S]
+    push_dst: torch.Tensor                # int64 [S]: row in the destination's [local | halo] buffer
+    stage_ptr: np.ndarray                 # int64 [n_stages + 1] (host)
+
+
+def edge_balanced_bounds(rowptr: np.ndarray, n_blocks: int) -> List[int]:
+    """Contiguous row blocks holding ~equal numbers of edges (the last block takes the remainder)."""
+    n = rowptr.shape[0] - 1
+    total = int(rowptr[-1])
+    if n_blocks <= 1 or n == 0:
+        return [0, n]
+    targets = np.asarray([total * k // n_blocks for k in range(1, n_blocks)], dtype=np.int64)
+    cuts = np.clip(np.searchsorted(rowptr, targets, side="left"), 0, n).tolist()
+    bounds = [0]
+    for c in cuts:
+        bounds.append(max(int(c), bounds[-1]))
+    bounds.append(n)
+    return bounds
+
+
+def build_stage_plan(hp: HaloPlan, n_stages: int, group=None, seg_len: int = ops.DEFAULT_SEG_LEN) -> StagePlan:
+    """Cut the rank's rows into `n_stages` edge-balanced blocks, tag every halo row with the first block
+    that reads it (gae_halo_stage_tags_host), tell the owners, and build the staged send lists
+    (gae_halo_push_lists_host)."""
+    lib = _lib.load()
+    dev = hp.rowptr.device
+    world, rank = hp.world, hp.rank
+    n_stages = max(1, min(int(n_stages), 32))
+    rp = hp.rowptr.cpu().numpy()
+    cl = hp.col.cpu().numpy()
+    bounds = edge_balanced_bounds(rp, n_stages)
+    n_stages = len(bounds) - 1
+    rb = np.asarray(bounds, dtype=np.int64)
+    halo_stage = np.zeros(max(hp.n_halo, 1), dtype=np.int32)
+    _lib.check(lib.gae_halo_stage_tags_host(_np_ptr(rp), _np_ptr(cl), hp.n_local, hp.n_halo, _np_ptr(rb), n_stages,
+                                            _np_ptr(halo_stage)), "gae_halo_stage_tags_host")
+    halo_stage = halo_stage[:hp.n_halo]
+    # tell every owner the stage of each row it sends me (same order as the request lists)
+    hs = torch.from_numpy(halo_stage).to(dev)
+    send_stage = torch.empty(int(hp.send_idx.numel()), dtype=torch.int32, device=dev)
+    all_to_all_v(send_stage, hs, hp.send_counts, hp.recv_counts, group)
+    # where my rows land in each peer's buffer: peer q keeps the rows owned by rank r at halo offset cuts_q[r]
+    cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+    cuts[1:] = torch.cumsum(torch.tensor(hp.recv_counts, dtype=torch.int64, device=dev), 0)
+    mine_at_peer = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(mine_at_peer, (cuts[:-1] + hp.n_local).contiguous(), group=group)
+    m = int(hp.send_idx.numel())
+    send_idx = np.ascontiguousarray(hp.send_idx.cpu().numpy(), dtype=np.int64)
+    sst = np.ascontiguousarray(send_stage.cpu().numpy(), dtype=np.int32)
+    sc = np.asarray(hp.send_counts, dtype=np.int64)
+    base = np.ascontiguousarray(mine_at_peer.cpu().numpy(), dtype=np.int64)
+    o_src, o_peer, o_dst = (np.zeros(max(m, 1), dtype=np.int64), np.zeros(max(m, 1), dtype=np.int32),
+                            np.zeros(max(m, 1), dtype=np.int64))
+    stage_ptr = np.zeros(n_stages + 1, dtype=np.int64)
+    _lib.check(lib.gae_halo_push_lists_host(_np_ptr(send_idx), _np_ptr(sst), _np_ptr(sc), _np_ptr(base), world, n_stages,
+                                            _np_ptr(o_src), _np_ptr(o_peer), _np_ptr(o_dst), _np_ptr(stage_ptr)),
+               "gae_halo_push_lists_host")
+    # row-block sub-CSRs (views of the local CSR; only rowptr is rebased)
+    sub_rowptr, sub_col, sub_plan = [], [], []
+    for s in range(n_stages):
+        r0, r1 = bounds[s], bounds[s + 1]
+        e0, e1 = int(rp[r0]), int(rp[r1])
+        srp = (hp.rowptr[r0:r1 + 1] - e0).contiguous()
+        scl = hp.col[e0:e1]
+        plan = None
+        if srp.is_cuda and r1 > r0:
+            plan = ops.build_hub_plan(srp, seg_len)
+            ops.order_segments_by_source(plan, srp, scl)
+        sub_rowptr.append(srp)
+        sub_col.append(scl)
+        sub_plan.append(plan)
+    return StagePlan(n_stages, bounds, sub_rowptr, sub_col, sub_plan, torch.from_numpy(halo_stage.copy()),
+                     torch.from_numpy(sst.copy()), torch.from_numpy(o_src[:m]).to(dev), torch.from_numpy(o_peer[:m]).to(dev),
+                     torch.from_numpy(o_dst[:m]).to(dev), stage_ptr)
+
+
+# ------------------------------------------------------------------------------------------------
+# peer memory (CUDA IPC) shared by the operators of one process
+# ------------------------------------------------------------------------------------------------
+
+FLAG_WORDS = 1024          # GAE_HALO_FLAG_WORDS
+FLAG_BLOCKS = 64
+
+
+class PeerMemory:
+    """CUDA IPC mappings of this process: every peer allocation is opened once (opening the same
+    handle twice in one process fails) and one flag pool serves all partitioned operators."""
+    _by_group: Dict[int, "PeerMemory"] = {}
+
+    @classmethod
+    def get(cls, device, group=None) -> "PeerMemory":
+        key = id(group)
+        pm = cls._by_group.get(key)
+        if pm is None or pm.device != device:
+            pm = cls(device, group)
+            cls._by_group[key] = pm
+        return pm
+
+    def __init__(self, device, group=None):
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._opened: Dict[tuple, int] = {}
+        self.flag_pool = torch.zeros(FLAG_BLOCKS * FLAG_WORDS, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)                     # zeros are in memory before any peer writes a flag
+        self._flag_bases = self.map(self.flag_pool)
+        self._next_block = 0
+
+    def map(self, t: torch.Tensor) -> List[int]:
+        """Addresses of tensor `t` (same role on every rank, collective call) in this process."""
+        lib = _lib.load()
+        handle = (ctypes.c_uint8 * 64)()
+        off = ctypes.c_int64(0)
+        _lib.check(lib.gae_ipc_get_handle(ctypes.c_void_p(t.data_ptr()), ctypes.byref(handle), ctypes.byref(off)),
+                   "gae_ipc_get_handle")
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=self.group)
+        ptrs = []
+        for r, (h, o) in enumerate(everyone):
+            if r == self.rank:
+                ptrs.append(t.data_ptr())
+                continue
+            base = self._opened.get((r, h))
+            if base is None:
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(h)
+                out = ctypes.c_void_p()
+                _lib.check(lib.gae_ipc_open_handle(ctypes.byref(buf), ctypes.byref(out)), "gae_ipc_open_handle")
+                base = int(out.value)
+                self._opened[(r, h)] = base
+            ptrs.append(base + o)
+        return ptrs
+
+    def flag_block(self):
+        """(my block as an int64 view, its address on every rank); collective: every rank takes the
+        same block index."""
+        k = self._next_block
+        if k >= FLAG_BLOCKS:
+            raise GaeError("PeerMemory: out of flag blocks")
+        self._next_block += 1
+        mine = self.flag_pool[k * FLAG_WORDS:(k + 1) * FLAG_WORDS]
+        return mine, [b + k * FLAG_WORDS * 8 for b in self._flag_bases]
+
+
+class HaloSpMM:
+    """Y_local = (A X)[my rows]: staged one-sided halo push overlapped with the row-block SpMMs, the
+    whole operator behind one C call (gae_halo_spmm_f32).  `X_ext` is the [n_local + n_halo, d]
+    feature buffer; callers write their rows into `X_local` on the current stream."""
+
+    exchange = "halo"
+
+    def __init__(self, hp: HaloPlan, d: int, n_stages: int = DEFAULT_STAGES, group=None, push_ctas: int = 0,
+                 push_threads: int = 0, timeout_ms: int = 0):
+        if d % 4 != 0:
+            raise GaeError("the halo exchange needs 16-byte rows (d a multiple of 4)")
+        self.hp, self.d, self.group = hp, d, group
+        dev = hp.rowptr.device
+        self.sp = sp = build_stage_plan(hp, n_stages, group)
+        self.X_ext = ops.alloc_rows(hp.n_local + hp.n_halo, d, dev)
+        self.Y = ops.alloc_rows(hp.n_local, d, dev)
+        n_seg = max([p.n_seg for p in sp.sub_plan if p is not None] + [0])
+        self.ws = torch.empty((max(n_seg, 1), ops.round_up4(d)), dtype=torch.float32, device=dev)
+        self.epoch = 0
+        self._comm = torch.cuda.Stream(device=dev)
+        ex = HaloExchangeStruct()
+        ex.world, ex.rank, ex.n_stages, ex.d = hp.world, hp.rank, sp.n_stages, d
+        ex.ld = self.X_ext.stride(0)
+        ex.x_local = self.X_ext.data_ptr()
+        if hp.world > 1:
+            pm = PeerMemory.get(dev, group)
+            lds = [None] * hp.world
+            dist.all_gather_object(lds, int(self.X_ext.stride(0)), group=group)
+            if any(x != lds[0] for x in lds):
+                raise GaeError("halo exchange needs the same feature row stride on every rank")
+            self._peer_x = torch.tensor(pm.map(self.X_ext), dtype=torch.int64, device=dev)
+            self.flags, flag_ptrs = pm.flag_block()
+            self._peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device=dev)
+        else:
+            self._peer_x = torch.tensor([self.X_ext.data_ptr()], dtype=torch.int64, device=dev)
+            self.flags = torch.zeros(FLAG_WORDS, dtype=torch.int64, device=dev)
+            self._peer_flags = torch.tensor([self.flags.data_ptr()], dtype=torch.int64, device=dev)
+        ex.peer_x, ex.peer_flags, ex.flags = self._peer_x.data_ptr(), self._peer_flags.data_ptr(), self.flags.data_ptr()
+        ex.send_src, ex.send_peer, ex.send_dst = sp.push_src.data_ptr(), sp.push_peer.data_ptr(), sp.push_dst.data_ptr()
+        ex.stage_ptr = sp.stage_ptr.ctypes.data
+        self._stage_done = torch.zeros(sp.n_stages, dtype=torch.int32, device=dev)
+        ex.stage_done = self._stage_done.data_ptr()
+        ex.push_ctas, ex.push_threads, ex.timeout_ms = int(push_ctas), int(push_threads), int(timeout_ms)
+        self._ex = ex
+        blocks = (HaloBlockStruct * sp.n_stages)()
+        for s in range(sp.n_stages):
+            blocks[s].row0, blocks[s].n_rows = sp.row_bounds[s], sp.row_bounds[s + 1] - sp.row_bounds[s]
+            blocks[s].rowptr, blocks[s].col = sp.sub_rowptr[s].data_ptr(), sp.sub_col[s].data_ptr()
+            p = sp.sub_plan[s]
+            if p is not None and (p.n_seg > 0 or p.bins is not None):
+                blocks[s].plan = ctypes.addressof(p.struct)
+            blocks[s].partial_ws = self.ws.data_ptr()
+        self._blocks = blocks
+        if hp.world > 1:
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)      # every rank's buffers and zeroed flags exist before the first push
+
+    @property
+    def X_local(self) -> torch.Tensor:
+        return self.X_ext[: self.hp.n_local]
+
+    @property
+    def X_halo(self) -> torch.Tensor:
+        return self.X_ext[self.hp.n_local:]
+
+    def __call__(self) -> torch.Tensor:
+        self.epoch += 1
+        rc = _lib.load().gae_halo_spmm_f32(ctypes.byref(self._ex), self._blocks, ctypes.c_void_p(self.Y.data_ptr()),
+                                           self.Y.stride(0), self.epoch, ops._stream(), self._comm.cuda_stream)
+        _lib.check(rc, "gae_halo_spmm_f32")
+        return self.Y
+
+    def check(self) -> None:
+        """Synchronous: raise if any flag wait of this operator timed out."""
+        t = ctypes.c_int64(0)
+        _lib.check(_lib.load().gae_halo_status(ctypes.byref(self._ex), ctypes.byref(t)), "gae_halo_status")
 
 
 class PartitionedSpMM:
@@ -147,29 +413,12 @@ class PartitionedSpMM:
 
     def _setup_p2p(self) -> None:
         """Map every peer's X_ext through CUDA IPC (one handle exchange per buffer)."""
-        import ctypes
-        from . import _lib
-        lib = _lib.load()
         hp = self.hp
-        handle = (ctypes.c_uint8 * 64)()
-        off = ctypes.c_int64(0)
-        _lib.check(lib.gae_ipc_get_handle(ctypes.c_void_p(self.X_ext.data_ptr()), ctypes.byref(handle),
-                                          ctypes.byref(off)), "gae_ipc_get_handle")
-        mine = (bytes(handle), int(off.value), int(self.X_ext.stride(0)))
-        everyone = [None] * hp.world
-        dist.all_gather_object(everyone, mine, group=self.group)
-        ptrs, self._opened = [], []
-        for r, (h, o, ld) in enumerate(everyone):
-            if ld != self.X_ext.stride(0):
-                raise GaeError("p2p exchange needs the same feature row stride on every rank")
-            if r == hp.rank:
-                ptrs.append(self.X_ext.data_ptr())
-                continue
-            buf = (ctypes.c_uint8 * 64).from_buffer_copy(h)
-            base = ctypes.c_void_p()
-            _lib.check(lib.gae_ipc_open_handle(ctypes.byref(buf), ctypes.byref(base)), "gae_ipc_open_handle")
-            self._opened.append(base.value)
-            ptrs.append(base.value + o)
+        lds = [None] * hp.world
+        dist.all_gather_object(lds, int(self.X_ext.stride(0)), group=self.group)
+        if any(x != lds[0] for x in lds):
+            raise GaeError("p2p exchange needs the same feature row stride on every rank")
+        ptrs = PeerMemory.get(self.X_ext.device, self.group).map(self.X_ext)
         dev = self.X_ext.device
         self._peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         b = torch.tensor(hp.bounds, dtype=torch.int64, device=dev)
@@ -319,7 +568,11 @@ class RmatPartition:
 
 
 def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device, exchange: str = "auto",
-                         group=None, stages: int = 1) -> RmatPartition:
+                         group=None, stages: int = DEFAULT_STAGES, push_ctas: int = 0) -> RmatPartition:
+    """Distributed R-MAT workload: every rank draws 1/P of the edge stream, edges are routed to the owner
+    of their row, and the forward (rows = dst) and backward (rows = src) partitioned operators are built.
+    exchange: "halo" (staged one-sided push with device flags, overlapped with `stages` row blocks),
+    "nccl", "push", "p2p"; "auto" = halo, falling back to nccl collectively when CUDA IPC is unavailable."""
     from . import synthetic
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = 1 << scale
@@ -330,7 +583,7 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     src, dst = synthetic.rmat_edges(scale, count, seed=seed, device=device, first_edge=first)
     requested = exchange
     if exchange == "auto":
-        exchange = "push"         # one-sided push (posted NVLink stores) is the fastest mechanism (profiles/)
+        exchange = "halo"
     # forward: rows = dst
     fs, fd = route_edges(src, dst, dst, bounds, group)
     hp_f = build_halo_plan(fs, fd, n, rank, world, group)
@@ -341,22 +594,27 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     hp_b = build_halo_plan(bs, bd, n, rank, world, group)
     del bs, bd
     torch.cuda.empty_cache()
+
     def make_ops(mode):
+        if mode == "halo":
+            return (HaloSpMM(hp_f, d, stages, group, push_ctas=push_ctas),
+                    HaloSpMM(hp_b, d, stages, group, push_ctas=push_ctas))
         return PartitionedSpMM(hp_f, d, mode, group), PartitionedSpMM(hp_b, d, mode, group)
 
     if requested == "auto":
         # CUDA IPC needs peer access between every pair of GPUs; agree collectively, else use NCCL
+        err = None
         try:
-            fwd_op, bwd_op = make_ops("push")
+            fwd_op, bwd_op = make_ops("halo")
             ok = 1
-        except Exception as exc:  # noqa: BLE001
+        except GaeError as exc:
             fwd_op = bwd_op = None
-            ok = 0
-            if rank == 0:
-                print(f"[gae_dgl_b200.parallel] p2p exchange unavailable ({exc}); using NCCL all-to-all-v")
+            ok, err = 0, exc
         flag = torch.tensor([ok], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag) == 0:
+            if rank == 0:
+                print(f"[gae_dgl_b200.parallel] one-sided halo exchange unavailable ({err}); using NCCL all-to-all-v")
             exchange = "nccl"
             del fwd_op, bwd_op
             fwd_op, bwd_op = make_ops("nccl")
@@ -365,29 +623,10 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     lo = bounds[rank]
     fwd_op.X_local.copy_(synthetic.hashed_normal(hp_f.n_local, d, 2, device=device, first_row=lo))
     bwd_op.X_local.copy_(synthetic.hashed_normal(hp_b.n_local, d, 3, device=device, first_row=lo))
-    if stages > 1 and exchange in ("push", "nccl"):
-        # experimental (parallel_staged.py): B exchange stages overlapped with B row-block SpMMs
-        from .parallel_staged import StagedPartitionedSpMM
-        fwd_op = _StagedAdapter(StagedPartitionedSpMM(fwd_op, stages, group))
-        bwd_op = _StagedAdapter(StagedPartitionedSpMM(bwd_op, stages, group))
     desc = {"nccl": "pack + NCCL all-to-all-v of deduplicated halo rows, per SpMM",
-            "push": "one-sided push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores), per SpMM",
-            "p2p": "one-sided pull of deduplicated halo rows from peer HBM (CUDA IPC over NVLink), per SpMM"}[exchange]
-    if stages > 1:
-        desc += f"; {stages} exchange stages pipelined with row-block SpMMs"
+            "push": "one-sided push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores) between two NCCL barriers, per SpMM",
+            "p2p": "one-sided pull of deduplicated halo rows from peer HBM (CUDA IPC over NVLink), per SpMM",
+            "halo": f"one-sided staged push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores, "
+                    f"device-side release/acquire flags, no collective), {fwd_op.sp.n_stages if exchange == 'halo' else 0} "
+                    "stages overlapped with the row-block SpMMs, per SpMM"}[exchange]
     return RmatPartition(fwd_op, bwd_op, hp_f.n_edges, hp_f.n_local, hp_f.n_halo, desc, total_edges, d)
-
-
-class _StagedAdapter:
-    """Gives a StagedPartitionedSpMM the attribute surface RmatPartition uses (X_ext, X_local, call)."""
-
-    def __init__(self, staged):
-        self.staged = staged
-        self.X_ext = staged.base.X_ext
-
-    @property
-    def X_local(self):
-        return self.staged.base.X_local
-
-    def __call__(self):
-        return self.staged()

@@ -35,6 +35,7 @@ extern "C" {
 #define GAE_ERR_INVALID_ARG (-1)
 #define GAE_ERR_UNSUPPORTED (-2)
 #define GAE_ERR_WORKSPACE (-3)
+#define GAE_ERR_TIMEOUT (-4)
 
 #define GAE_ACT_IDENTITY 0 /* gae.py:43,45  lambda x: x */
 #define GAE_ACT_RELU 1     /* gae.py:36-41  F.relu      */
@@ -257,6 +258,78 @@ int gae_push_rows_p2p_f32(const float *X, int64_t ldx, const int64_t *send_idx,
 int gae_ipc_get_handle(const void *dev_ptr, uint8_t handle_out[64], int64_t *offset_out);
 int gae_ipc_open_handle(const uint8_t handle[64], void **dev_ptr_out);
 int gae_ipc_close_handle(void *dev_ptr);
+
+/* ---- K7b: staged halo exchange fused with the row-block SpMMs (8e; the default multi-GPU path) ---- */
+/* Device-side protocol, no collective and no host sync on the data path.  Every rank maps its peers'
+ * [local | halo] feature buffers and one FLAG block (GAE_HALO_FLAG_WORDS uint64, zero-initialised once)
+ * per partitioned operator through CUDA IPC (gae_ipc_*).  Halo rows are tagged with the first row block
+ * ("stage") of the consumer that reads them.  Per SpMM and rank:
+ *   gae_halo_push_f32     one persistent kernel: waits until every peer has consumed epoch-1, then pushes
+ *                         the rows of stage 0, 1, ... into the peers' halo regions (posted NVLink stores)
+ *                         and publishes landed[rank][stage] = epoch to every peer after each stage;
+ *   gae_halo_wait_f32     one-warp kernel: acquires landed[q][stage] >= epoch from all peers q;
+ *   gae_halo_release_f32  publishes consumed[rank] = epoch to every peer (my halo may be overwritten);
+ *   gae_halo_spmm_f32     the whole operator Y = (A X)[my rows]: push on comm_stream, and on
+ *                         compute_stream for s = 0..n_stages-1 { wait(s); SpMM of row block s } + release,
+ *                         so the transfer of later stages overlaps the aggregation of earlier ones.
+ * `epoch` counts the calls on one operator from 1.  Flag waits are bounded by timeout_ms (default 10 s):
+ * on expiry an error word is set and the kernel falls through -- gae_halo_status() reports it -- so a
+ * protocol fault gives a wrong, reported result and never a hung GPU.  Replaces nothing in the reference
+ * (single device, train_inductive.py:26,29); it is how update_all (gae.py:28) spans the GPUs of a box. */
+#define GAE_HALO_MAX_WORLD 16
+#define GAE_HALO_MAX_STAGES 32
+#define GAE_HALO_FLAG_WORDS 1024
+typedef struct gae_halo_exchange_t {
+    int32_t world, rank, n_stages, d;
+    int64_t ld;                   /* row stride (floats) of EVERY rank's [local | halo] buffer          */
+    const float *x_local;         /* my [local | halo] buffer (device)                                  */
+    float *const *peer_x;         /* DEVICE array [world]: that buffer of every rank, IPC-mapped        */
+    uint64_t *const *peer_flags;  /* DEVICE array [world]: this operator's flag block on every rank     */
+    uint64_t *flags;              /* my flag block (device)                                             */
+    const int64_t *send_src;      /* DEVICE [m]: local row of each entry, sorted by stage               */
+    const int32_t *send_peer;     /* DEVICE [m]: destination rank                                       */
+    const int64_t *send_dst;      /* DEVICE [m]: row in the destination's buffer                        */
+    const int64_t *stage_ptr;     /* HOST [n_stages+1]: entry range of each stage                       */
+    uint32_t *stage_done;         /* DEVICE [n_stages]: zero-initialised arrival counters (scratch)     */
+    int32_t push_ctas;            /* 0 = default (64)                                                   */
+    int32_t push_threads;         /* 0 = default (512)                                                  */
+    int32_t timeout_ms;           /* 0 = default (10000)                                                */
+} gae_halo_exchange_t;
+typedef struct gae_halo_block_t {
+    int64_t row0, n_rows;         /* local row range of the block                                       */
+    const int64_t *rowptr;        /* DEVICE [n_rows+1], rebased to 0                                    */
+    const int32_t *col;           /* DEVICE: the block's slice of the [local | halo] column array       */
+    const gae_hub_plan_t *plan;   /* hub plan of the block (may be NULL)                                */
+    float *partial_ws;            /* its segment workspace                                              */
+} gae_halo_block_t;
+int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
+int gae_halo_wait_f32(const gae_halo_exchange_t *ex, int32_t stage, uint64_t epoch, void *stream);
+int gae_halo_release_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
+int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_block_t *blocks /* HOST [n_stages] */,
+                      float *Y, int64_t ldy, uint64_t epoch, void *compute_stream, void *comm_stream);
+/* Synchronous: copies the error word back; GAE_ERR_TIMEOUT if any flag wait expired since start. */
+int gae_halo_status(const gae_halo_exchange_t *ex, int64_t *timeouts);
+
+/* Halo planning on HOST arrays, O(E + V/64).  src_global[E]: global source id of every edge whose row
+ * this rank owns; bounds[world+1]: contiguous vertex blocks.  Two-call protocol:
+ *   count -> n_halo, recv_counts[world] (halo rows owned by each peer)
+ *   fill  -> halo_ids[n_halo] (ascending = grouped by owner), col_local[E] = column in [local | halo] */
+int gae_halo_plan_count_host(const int64_t *src_global, int64_t n_edges, const int64_t *bounds,
+                             int32_t world, int32_t rank, int64_t *n_halo, int64_t *recv_counts);
+int gae_halo_plan_fill_host(const int64_t *src_global, int64_t n_edges, const int64_t *bounds,
+                            int32_t world, int32_t rank, int64_t *halo_ids, int32_t *col_local);
+/* halo_stage[h] = first row block (row_bounds[n_stages+1] over the local rows) that reads halo row h. */
+int gae_halo_stage_tags_host(const int64_t *rowptr, const int32_t *col_local, int64_t n_local,
+                             int64_t n_halo, const int64_t *row_bounds, int32_t n_stages,
+                             int32_t *halo_stage);
+/* Send lists of the push kernel.  send_idx: my local rows requested by the peers, grouped by peer in
+ * request order (send_counts[world]); send_stage: the stage of each entry at its consumer (NULL = 0);
+ * dst_base[q]: row in q's buffer where my first row lands.  Output: entries sorted by stage and, within
+ * a stage, interleaved over the peers; stage_ptr[n_stages+1]. */
+int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *send_stage,
+                             const int64_t *send_counts, const int64_t *dst_base, int32_t world,
+                             int32_t n_stages, int64_t *out_src, int32_t *out_peer, int64_t *out_dst,
+                             int64_t *stage_ptr);
 
 /* ---- optimiser step (train_inductive.py:40,52: torch.optim.Adam, no weight decay / amsgrad) ---- */
 /* One launch over up to GAE_ADAM_MAX_TENSORS parameter tensors (device pointers passed in HOST arrays):

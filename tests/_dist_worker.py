@@ -55,21 +55,48 @@ def run(rank, world, port, scale, n_edges, d, result_dir):
             assert torch.equal(op.X_halo, Xg[plan.halo_ids])
             assert sum(plan.recv_counts) == plan.n_halo and int(plan.col.max()) < plan.n_local + plan.n_halo
             out[name] = Y
-            # staged exchange pipelined with row-block SpMM (parallel_staged): same result, and block b
-            # reads only halo rows that stages <= b have delivered (the halo is poisoned beforehand)
-            from gae_dgl_b200 import parallel_staged as PS
+            # staged one-sided exchange (HaloSpMM's plan, built by the gae_halo_*_host helpers): the push
+            # lists are executed here by a gloo emulation of the push kernel (entries grouped by peer,
+            # rows + destination indices through all-to-all-v), stage by stage, followed by the row-block
+            # SpMM of that stage.  Same result as the unstaged op, and block b reads only halo rows that
+            # stages <= b have delivered (the halo is poisoned beforehand).
             for n_stages in (1, 2, 4, 7):
-                st = PS.StagedPartitionedSpMM(op, n_stages, overlap=False)
-                sp = st.sp
+                sp = parallel.build_stage_plan(plan, n_stages)
                 assert sp.row_bounds[0] == 0 and sp.row_bounds[-1] == plan.n_local
-                assert sorted(torch.cat(sp.recv_pos).tolist()) == list(range(plan.n_halo))      # every halo row once
-                assert sum(int(i.numel()) for i in sp.send_idx) == int(plan.send_idx.numel())
-                edges_per_block = [int(r[-1]) for r in sp.sub_rowptr]
-                assert sum(edges_per_block) == plan.n_edges
+                assert int(sp.stage_ptr[0]) == 0 and int(sp.stage_ptr[-1]) == int(plan.send_idx.numel())
+                assert sorted(sp.push_src.tolist()) == sorted(plan.send_idx.tolist())
+                assert sum(int(r[-1]) for r in sp.sub_rowptr) == plan.n_edges
                 op.X_halo.fill_(float("nan"))
                 op.Y.fill_(float("nan"))
-                Ys = st()
-                assert torch.equal(Ys, Y), (name, n_stages)
+                landed = torch.zeros(plan.n_local + plan.n_halo, dtype=torch.int32)
+                for st in range(sp.n_stages):
+                    e0, e1 = int(sp.stage_ptr[st]), int(sp.stage_ptr[st + 1])
+                    peer = sp.push_peer[e0:e1].to(torch.int64)
+                    # interleaving: within a stage consecutive entries cycle over the peers that still have rows
+                    if e1 - e0 > world:
+                        assert len(set(peer[:min(world - 1, e1 - e0)].tolist())) == min(world - 1, len(set(peer.tolist())))
+                    order = torch.argsort(peer, stable=True)
+                    cnt = torch.bincount(peer, minlength=world)
+                    rcnt = torch.empty_like(cnt)
+                    dist.all_to_all_single(rcnt, cnt)
+                    rows = op.X_local.index_select(0, sp.push_src[e0:e1][order])
+                    dsts = sp.push_dst[e0:e1][order].contiguous()
+                    got_rows = torch.empty((int(rcnt.sum()), d))
+                    got_dst = torch.empty(int(rcnt.sum()), dtype=torch.int64)
+                    parallel.all_to_all_v(got_rows, rows, rcnt.tolist(), cnt.tolist())
+                    parallel.all_to_all_v(got_dst, dsts, rcnt.tolist(), cnt.tolist())
+                    assert got_dst.numel() == 0 or (int(got_dst.min()) >= plan.n_local and
+                                                    int(got_dst.max()) < plan.n_local + plan.n_halo)
+                    op.X_ext[got_dst] = got_rows
+                    landed[got_dst] += 1
+                    assert torch.equal(sp.halo_stage[got_dst - plan.n_local].to(torch.int64),
+                                       torch.full_like(got_dst, st))
+                    r0, r1 = sp.row_bounds[st], sp.row_bounds[st + 1]
+                    if r1 > r0:
+                        _cpu_spmm(sp.sub_rowptr[st], sp.sub_col[st], op.X_ext, None, op.Y[r0:r1], None)
+                    assert not torch.isnan(op.Y[:r1]).any(), (name, n_stages, st)
+                assert torch.equal(landed[plan.n_local:], torch.ones(plan.n_halo, dtype=torch.int32))   # every halo row once
+                assert torch.equal(op.Y, Y), (name, n_stages)
                 assert torch.equal(op.X_halo, Xg[plan.halo_ids])
                 # first-use tags: a halo row's stage is the block of the first local row that references it
                 deg = plan.rowptr[1:] - plan.rowptr[:-1]

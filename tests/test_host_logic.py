@@ -361,3 +361,67 @@ def test_native_adam_formula_matches_torch_optim():
         assert float((p - p_ref.detach()).abs().max()) < 2e-6 * max(1.0, float(p_ref.abs().max())), step
     st = opt.state[p_ref]
     assert float((m - st["exp_avg"]).abs().max()) < 1e-6 and float((v - st["exp_avg_sq"]).abs().max()) < 1e-6
+
+
+# ---- halo planning helpers of the C ABI (host side; the kernels are covered by the -m gpu / N>1 runs) ------------
+
+def test_halo_plan_host_matches_index_algebra(lib_built):
+    """gae_halo_plan_count/fill_host against the definition: halo = sorted unique remote sources, columns
+    remapped to [local | halo], per-owner counts from the block bounds."""
+    from gae_dgl_b200 import parallel
+    rng = np.random.default_rng(0)
+    n, world = 1000, 4
+    bounds = parallel.block_bounds(n, world)
+    for rank in range(world):
+        lo, hi = bounds[rank], bounds[rank + 1]
+        src = rng.integers(0, n, size=5000).astype(np.int64)
+        halo, col, recv = parallel.halo_plan_host(src, bounds, rank)
+        remote = (src < lo) | (src >= hi)
+        want_halo = np.unique(src[remote])
+        assert np.array_equal(halo, want_halo)
+        want_col = np.where(remote, (hi - lo) + np.searchsorted(want_halo, src), src - lo)
+        assert np.array_equal(col, want_col.astype(np.int32))
+        assert recv == [int(((want_halo >= bounds[q]) & (want_halo < bounds[q + 1])).sum()) for q in range(world)]
+        assert recv[rank] == 0
+    # no edges / no remote sources
+    halo, col, recv = parallel.halo_plan_host(np.zeros(0, dtype=np.int64), bounds, 1)
+    assert halo.size == 0 and col.size == 0 and recv == [0] * world
+    halo, col, recv = parallel.halo_plan_host(np.arange(bounds[1], bounds[2], dtype=np.int64), bounds, 1)
+    assert halo.size == 0 and np.array_equal(col, np.arange(bounds[2] - bounds[1], dtype=np.int32))
+    # out-of-range source id is rejected
+    with pytest.raises(_lib.GaeError):
+        parallel.halo_plan_host(np.asarray([n], dtype=np.int64), bounds, 0)
+
+
+def test_halo_stage_tags_and_push_lists_host(lib_built):
+    lib = _lib.load()
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    # 4 local rows, 3 halo rows (columns 4, 5, 6); two row blocks [0,2) and [2,4)
+    rowptr = np.asarray([0, 2, 3, 5, 7], dtype=np.int64)
+    col = np.asarray([0, 5, 1, 4, 5, 2, 6], dtype=np.int32)
+    tags = np.full(3, 9, dtype=np.int32)
+    rb = np.asarray([0, 2, 4], dtype=np.int64)
+    _lib.check(lib.gae_halo_stage_tags_host(P(rowptr), P(col), 4, 3, P(rb), 2, P(tags)), "tags")
+    assert tags.tolist() == [1, 0, 1]
+    # an unreferenced halo row is an error
+    assert lib.gae_halo_stage_tags_host(P(rowptr), P(col), 4, 4, P(rb), 2, P(np.zeros(4, dtype=np.int32))) == -1
+    # push lists: 3 peers, I am rank 1; peer 0 asks rows [7, 8, 9] (stages 0, 1, 0), peer 2 asks [3, 4] (stages 0, 0)
+    send_idx = np.asarray([7, 8, 9, 3, 4], dtype=np.int64)
+    stage = np.asarray([0, 1, 0, 0, 0], dtype=np.int32)
+    counts = np.asarray([3, 0, 2], dtype=np.int64)
+    base = np.asarray([100, 0, 200], dtype=np.int64)
+    o_src, o_peer, o_dst = np.zeros(5, dtype=np.int64), np.zeros(5, dtype=np.int32), np.zeros(5, dtype=np.int64)
+    sptr = np.zeros(3, dtype=np.int64)
+    _lib.check(lib.gae_halo_push_lists_host(P(send_idx), P(stage), P(counts), P(base), 3, 2, P(o_src), P(o_peer), P(o_dst),
+                                            P(sptr)), "push lists")
+    assert sptr.tolist() == [0, 4, 5]
+    # stage 0 interleaves the peers (k-th entry of each), stage 1 follows; dst = base[peer] + position in the request list
+    assert o_src.tolist() == [7, 3, 9, 4, 8]
+    assert o_peer.tolist() == [0, 2, 0, 2, 0]
+    assert o_dst.tolist() == [100, 200, 102, 201, 101]
+    assert lib.gae_halo_push_lists_host(P(send_idx), P(np.asarray([0, 2, 0, 0, 0], dtype=np.int32)), P(counts), P(base), 3,
+                                        2, P(o_src), P(o_peer), P(o_dst), P(sptr)) == -1
+    # descriptor validation happens before any launch (no GPU needed)
+    ex = _lib.HaloExchangeStruct()
+    assert lib.gae_halo_push_f32(ctypes.byref(ex), 1, None) == -1
+    assert lib.gae_halo_wait_f32(None, 0, 1, None) == -1

@@ -21,11 +21,24 @@ def main():
     scale, n_edges, d = 16, 2_000_000, 64
     n = 1 << scale
     ok = True
-    # (exchange, stages): stages > 1 = parallel_staged (exchange pipelined with row-block SpMMs)
-    for exchange, stages in (("nccl", 1), ("p2p", 1), ("push", 1), ("push", 4), ("nccl", 3)):
+    # (exchange, stages): "halo" = staged one-sided push with device flags, overlapped with `stages` row blocks
+    for exchange, stages in (("halo", 1), ("halo", 4), ("halo", 8), ("nccl", 1), ("push", 1), ("p2p", 1)):
         part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange, stages=stages)
         Yf = part.fwd().clone()
         Yb = part.bwd().clone()
+        if exchange == "halo":
+            # epochs 2..4: the flags must order successive calls as well (write-after-read on the halo region);
+            # the local rows are changed and restored in between so that a stale halo row would show
+            for k in range(3):
+                part.fwd_op.X_local.mul_(2.0 if k == 0 else 1.0)
+                part.fwd()
+                part.bwd()
+            part.fwd_op.X_local.mul_(0.5)
+            Yf2 = part.fwd().clone()
+            torch.cuda.synchronize()
+            part.fwd_op.check()
+            part.bwd_op.check()
+            assert torch.equal(Yf, Yf2), "halo exchange: a later epoch differs from the first"
         torch.cuda.synchronize()
         bounds = parallel.block_bounds(n, world)
         lo, hi = bounds[rank], bounds[rank + 1]
@@ -42,7 +55,6 @@ def main():
               f"local_rows={part.local_rows} local_edges={part.local_edges}", flush=True)
         ok = ok and ef < 1e-5 and eb < 1e-5
         del part
-        torch.cuda.empty_cache()
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
