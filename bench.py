@@ -46,7 +46,9 @@ def parse_args():
     p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     p.add_argument("--base-scale", type=int, default=BASE_SCALE, help="log2 |V| per GPU")
     p.add_argument("--base-edges", type=int, default=BASE_EDGES, help="|E| per GPU")
-    p.add_argument("--cpu-sample-div", type=int, default=8, help="CPU legs use |E|/div edges of the same stream")
+    p.add_argument("--strong", action="store_true",
+                   help="strong scaling: the FIXED configs[4] graph (scale 25, 8e8 edges) on N GPUs instead of 1e8 edges per GPU")
+    p.add_argument("--cpu-seconds", type=float, default=45.0, help="time budget of a CPU leg's timed steps (full workload)")
     p.add_argument("--no-pubmed", action="store_true")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
@@ -131,55 +133,89 @@ class ClockSampler:
 # CPU legs (oracle)
 # ------------------------------------------------------------------------------------------
 
-def cpu_rmat_leg(scale: int, sample_edges: int, steps: int, warmup: int, total_edges: int):
-    """Times the oracle's SpMM fwd + bwd (the reference's update_all(copy_src,sum) and its
-    adjoint) on the first `sample_edges` edges of the workload's edge stream, all host threads.
-    Two restatements are timed -- torch.sparse CSR (MKL) and the OpenMP C loop -- the faster is
-    reported."""
+def workload_of(args, n_gpus: int):
+    """(scale, total_edges, scaling): BASELINE.json configs[3] at N = 1 and configs[4] at N = 8 with 1e8 edges per GPU
+    in between (weak), or the fixed configs[4] graph at every N (--strong)."""
+    if args.strong:
+        return 25, 800_000_000, "strong"
+    return args.base_scale + int(round(math.log2(n_gpus))), args.base_edges * n_gpus, "weak"
+
+
+def config_of(scale: int, total_edges: int):
+    """The workload description shared by both arms (identical dicts => the driver's same_config check)."""
+    n = 1 << scale
+    return {"workload": f"rmat_scale{scale}_E{total_edges}_d{D_FEAT}", "step": "spmm_fwd+spmm_bwd",
+            "rmat": "a=.57 b=.19 c=.19 d=.05, no dedup, labels scrambled, seed 1",
+            "l2": f"inputs {4 * D_FEAT * n / 1e6:.0f} MB features + {4 * total_edges / 1e6:.0f} MB indices per SpMM "
+                  ">> 126 MB L2, no flush between iterations"}
+
+
+def host_csr_pair(scale: int, n_edges: int):
+    """CSR and CSR^T of the whole workload as host numpy arrays.  Set-up only (untimed): the edge stream is
+    drawn and sorted with torch on the GPU when one is present (same bits as on the CPU, synthetic.py), which
+    keeps the full-size CPU leg inside a few minutes; nothing of this package's kernels is involved."""
     from gae_dgl_b200 import synthetic
     from gae_dgl_b200.graph import coo_to_csr_torch
+    n = 1 << scale
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    src, dst = synthetic.rmat_edges(scale, n_edges, seed=1, device=dev)
+    out = []
+    for a, b in ((src, dst), (dst, src)):
+        rowptr, col = coo_to_csr_torch(a, b, n)
+        out += [rowptr.cpu().numpy(), col.cpu().numpy()]
+        del rowptr, col
+    del src, dst
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_rmat_leg(scale: int, n_edges: int, budget_s: float, max_steps: int = 10):
+    """Times the oracle's SpMM fwd + bwd (the reference's update_all(copy_src,sum), gae.py:28, and its
+    adjoint, train_inductive.py:51) on the WHOLE workload -- every edge, every vertex -- with all host
+    threads.  Two restatements are timed, torch.sparse CSR (MKL) and the OpenMP C loop; the faster is
+    reported.  CPU steps are bounded by time, not by shrinking the graph."""
     from oracle import c_spmm
-    from oracle import gae_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = 1 << scale
-    src, dst = synthetic.rmat_edges(scale, sample_edges, seed=1, device="cpu")
-    rowptr, col = coo_to_csr_torch(src, dst, n)
-    rowptr_t, col_t = coo_to_csr_torch(dst, src, n)
-    del src, dst
+    rp, cl, rpt, clt = host_csr_pair(scale, n_edges)
     # feature VALUES do not affect timing; torch.rand is used on the host to keep set-up short
     X = torch.rand(n, D_FEAT, generator=torch.Generator().manual_seed(2))
     dY = torch.rand(n, D_FEAT, generator=torch.Generator().manual_seed(3))
-    rp, cl, rpt, clt = rowptr.numpy(), col.numpy(), rowptr_t.numpy(), col_t.numpy()
     Xn, dYn = X.numpy(), dY.numpy()
 
     def step_c():
         c_spmm.spmm_f32(rp, cl, Xn)
         c_spmm.spmm_f32(rpt, clt, dYn)
 
-    A = torch.sparse_csr_tensor(rowptr, col.to(torch.int64), torch.ones(col.numel()), size=(n, n))
-    At = torch.sparse_csr_tensor(rowptr_t, col_t.to(torch.int64), torch.ones(col_t.numel()), size=(n, n))
-
-    def step_torch():
-        A @ X
-        At @ dY
-
-    results = {}
-    for name, fn in (("openmp_c", step_c), ("torch_sparse_csr", step_torch)):
-        for _ in range(max(1, min(warmup, 2))):
-            fn()
+    def run(fn, budget):
+        fn()                                   # warm-up (page faults, thread pool)
         ts = []
-        for _ in range(steps):
+        t_end = time.perf_counter() + budget
+        while len(ts) < max_steps and (len(ts) < 2 or time.perf_counter() < t_end):
             t0 = time.perf_counter()
             fn()
             ts.append(time.perf_counter() - t0)
-        results[name] = statistics.median(ts)
+        return statistics.median(ts), len(ts)
+
+    results, counts = {}, {}
+    results["openmp_c"], counts["openmp_c"] = run(step_c, budget_s * 0.6)
+    if n_edges <= 200_000_000:                 # torch's CSR tensors need int64 columns: 3x the index memory
+        A = torch.sparse_csr_tensor(torch.from_numpy(rp), torch.from_numpy(cl).to(torch.int64), torch.ones(cl.size), size=(n, n))
+        At = torch.sparse_csr_tensor(torch.from_numpy(rpt), torch.from_numpy(clt).to(torch.int64), torch.ones(clt.size), size=(n, n))
+
+        def step_torch():
+            A @ X
+            At @ dY
+
+        results["torch_sparse_csr"], counts["torch_sparse_csr"] = run(step_torch, budget_s * 0.4)
     best = min(results, key=results.get)
     return {
-        "value": sample_edges / results[best], "unit": "edges/s", "cores": cores, "kind": "port",
-        "sample": f"first {sample_edges} of {total_edges} edges of the same R-MAT stream (scale {scale}, |V|={n}), "
-                  f"SpMM fwd+bwd d={D_FEAT}, {best}, median of {steps}",
-        "ms_per_step": results[best] * 1e3,
+        "value": n_edges / results[best], "unit": "edges/s", "cores": cores, "kind": "port",
+        "sample": f"the whole workload: all {n_edges} edges of the R-MAT stream (scale {scale}, |V|={n}), "
+                  f"SpMM fwd+bwd d={D_FEAT}, {best}, median of {counts[best]} steps",
+        "ms_per_step": results[best] * 1e3, "steps": counts[best],
         "variants_ms": {k: v * 1e3 for k, v in results.items()},
     }
 
@@ -221,21 +257,22 @@ def run_reference(args):
     if rank != 0:
         return
     n_gpus = args.gpus
-    scale = args.base_scale + int(round(math.log2(n_gpus)))
-    total = args.base_edges * n_gpus
-    sample = max(1, args.base_edges // args.cpu_sample_div)
-    leg = cpu_rmat_leg(scale, sample, args.steps, args.warmup, total)
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    scale, total, scaling = workload_of(args, n_gpus)
+    leg = cpu_rmat_leg(scale, total, args.cpu_seconds, max_steps=max(2, min(args.steps, 10)))
     line = {
         "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "edges/s", "n_gpus": n_gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"rmat_scale{scale}_E{total}_d{D_FEAT}", "step": "spmm_fwd+spmm_bwd",
-                   "note": "reference = CPU oracle port (DGL not installable: no wheel, no network)"},
+        "steps": leg["steps"], "warmup": 1, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(scale, total),
+        "note": "reference = CPU oracle port on the host cores (DGL not installable: no wheel, no network); "
+                f"steps bounded by --cpu-seconds {args.cpu_seconds:g}, the graph is the full workload",
         "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": leg["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "variants_ms": leg["variants_ms"],
     }
-    if not args.no_pubmed and n_gpus == 1:
+    if not args.no_pubmed and n_gpus == 1 and not args.strong:
         line["pubmed"] = cpu_pubmed_leg()
         line["zinc"] = cpu_zinc_leg()
     print(json.dumps(line), flush=True)
@@ -244,6 +281,37 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+
+def sampled_parity(rowptr, col, Y, seed, lo=0, n_local=None, halo_ids=None, n_sample=96):
+    """Oracle check inside the bench run: the result rows of a sample of this rank's vertices (its heaviest
+    hub rows, then evenly spaced ones) are recomputed on the host by the oracle's fp64-accumulating C loop
+    from the global definition Y[v] = sum_{u->v} X[u], with X regenerated from the vertex ids
+    (synthetic.hashed_normal_rows) -- independent of the exchange.  Returns max |dY| / max(|ref|, 1)."""
+    from gae_dgl_b200 import synthetic
+    from oracle import c_spmm
+    n_rows = rowptr.numel() - 1
+    n_local = n_rows if n_local is None else n_local
+    deg = rowptr[1:] - rowptr[:-1]
+    hubs = torch.topk(deg, min(8, n_rows)).indices
+    spaced = torch.arange(0, n_rows, max(1, n_rows // (n_sample - 8)), device=rowptr.device)[: n_sample - 8]
+    rows = torch.unique(torch.cat([hubs, spaced]))
+    starts, ends = rowptr[rows], rowptr[rows + 1]
+    lens = (ends - starts)
+    sub_rowptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rowptr.device)
+    sub_rowptr[1:] = torch.cumsum(lens, 0)
+    eidx = torch.repeat_interleave(starts - sub_rowptr[:-1], lens) + torch.arange(int(sub_rowptr[-1]), device=rowptr.device)
+    c = col[eidx].to(torch.int64)
+    if halo_ids is not None:
+        gid = torch.where(c < n_local, c + lo, halo_ids[(c - n_local).clamp_(min=0)])
+    else:
+        gid = c
+    uniq, inv = torch.unique(gid, return_inverse=True)
+    Xs = synthetic.hashed_normal_rows(uniq, D_FEAT, seed).cpu().numpy()
+    ref = c_spmm.spmm_f64acc(sub_rowptr.cpu().numpy(), inv.to(torch.int32).cpu().numpy(), Xs)
+    got = Y[rows].double().cpu().numpy()
+    err = float(np.abs(got - ref).max() / max(float(np.abs(ref).max()), 1.0))
+    return err, int(rows.numel()), int(lens.max())
+
 
 def cuda_time_ms(fn, steps, stream):
     """K calls bracketed by events on the launching stream; returns total ms."""
@@ -389,9 +457,8 @@ def run_ours(args):
         k, v = kv.split("=")
         _lib.set_tuning(k, int(v))
 
-    scale = args.base_scale + int(round(math.log2(world)))
+    scale, total_edges, scaling = workload_of(args, world)
     n = 1 << scale
-    total_edges = args.base_edges * world
     stream = torch.cuda.current_stream()
 
     if world == 1:
@@ -488,19 +555,37 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"rmat_scale{scale}_E{total_edges}_d{D_FEAT}", "step": "spmm_fwd+spmm_bwd",
-                   "rmat": "a=.57 b=.19 c=.19 d=.05, no dedup, labels scrambled, seed 1",
-                   "partition": "1d_vertex_blocks" if world > 1 else "single", "exchange": exchange_desc,
-                   "halo_rows_rank0": halo_rows,
-                   "l2": f"inputs {4 * D_FEAT * local_rows / 1e6:.0f} MB features + {4 * local_edges / 1e6:.0f} MB indices "
-                         ">> 126 MB L2, no flush between iterations",
-                   "tuning": {k: _lib.get_tuning(k) for k in ("spmm_unroll", "spmm_block", "spmm_cache",
-                                                              "spmm_rows_per_warp")}},
+        "config": config_of(scale, total_edges),
+        "impl_detail": {"partition": "1d_vertex_blocks" if world > 1 else "single", "exchange": exchange_desc,
+                        "halo_rows_rank0": halo_rows, "local_rows_rank0": local_rows, "local_edges_rank0": local_edges,
+                        "tuning": {k: _lib.get_tuning(k) for k in ("spmm_unroll", "spmm_block", "spmm_cache",
+                                                                   "spmm_rows_per_warp", "spmm_fused")}},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": sampler.summary(),
         "fwd_ms_max_over_ranks": fwd_mean, "bwd_ms_max_over_ranks": bwd_mean,
     }
+
+    # ---- parity, in the same run: sampled result rows of every rank against the host oracle
+    if world == 1:
+        ef = sampled_parity(c.rowptr, c.col, Y, 2)
+        eb = sampled_parity(t.rowptr, t.col, dX, 3)
+    else:
+        for op in (part.fwd_op, part.bwd_op):
+            if hasattr(op, "check"):
+                op.check()                       # raises if any device-side flag wait timed out
+        lo = part.fwd_op.hp.bounds[rank]
+        ef = sampled_parity(part.fwd_op.hp.rowptr, part.fwd_op.hp.col, part.fwd_op.Y, 2, lo, part.fwd_op.hp.n_local,
+                            part.fwd_op.hp.halo_ids)
+        eb = sampled_parity(part.bwd_op.hp.rowptr, part.bwd_op.hp.col, part.bwd_op.Y, 3, lo, part.bwd_op.hp.n_local,
+                            part.bwd_op.hp.halo_ids)
+    perr = torch.tensor([ef[0], eb[0]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
+    line["parity"] = {"fwd_max_err": float(perr[0]), "bwd_max_err": float(perr[1]), "tolerance": 1e-5,
+                      "ok": bool(perr.max() < 1e-5), "rows_per_rank": ef[1], "max_degree_checked_rank0": ef[2],
+                      "checker": "oracle/spmm_ref.c fp64-accumulating loop on sampled rows of every rank (hub rows included), "
+                                 "X regenerated from vertex ids; max over ranks"}
 
     # ---- e2e: host buffers through the C ABI entry point, copies inside the timed region
     if not args.no_e2e and world == 1:
@@ -511,8 +596,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         del X, dY
         torch.cuda.empty_cache()
-        sample = max(1, args.base_edges // args.cpu_sample_div)
-        leg = cpu_rmat_leg(scale, sample, 3, 1, total_edges)
+        del Y, dX, c, t, g, fwd, bwd, step
+        torch.cuda.empty_cache()
+        leg = cpu_rmat_leg(scale, total_edges, min(args.cpu_seconds, 20.0), max_steps=5)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if not args.no_pubmed:
             line["pubmed"] = pubmed_leg(dev)

@@ -128,7 +128,7 @@ SIGNATURES = {
     "gae_halo_wait_f32": (c_int, [POINTER(HaloExchangeStruct), c_int32, c_uint64, c_void_p]),
     "gae_halo_release_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
     "gae_halo_spmm_f32": (c_int, [POINTER(HaloExchangeStruct), POINTER(HaloBlockStruct), c_void_p, c_int64, c_uint64,
-                                  c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p]),
     "gae_halo_status": (c_int, [POINTER(HaloExchangeStruct), POINTER(c_int64)]),
     "gae_halo_plan_count_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, POINTER(c_int64), c_void_p]),
     "gae_halo_plan_fill_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

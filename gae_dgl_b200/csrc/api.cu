@@ -12,7 +12,8 @@ static std::atomic<int64_t> g_launches{0};
 // defaults (B200 sweeps, profiles/r01_sweep_*.json): register-gather variant, 4 gathers in flight per
 // lane at 40 registers (48 warps/SM), 64-thread CTAs, plain caching, warp per row; decoder dense pass with
 // both GEMMs on the tensor cores (dec_mma = 1)
-static std::atomic<int32_t> g_tuning[T_COUNT] = {{0}, {4}, {64}, {0}, {1}, {0}, {2}, {1}, {2}, {1}, {0}, {1}};
+// PER-THREAD: a sweep on one host thread never changes what another thread's calls launch
+static thread_local int32_t g_tuning[T_COUNT] = {0, 4, 64, 0, 1, 0, 2, 1, 2, 1, -1, 1};
 static const char *const g_tuning_names[T_COUNT] = {"spmm_variant", "spmm_unroll", "spmm_block",
                                                      "spmm_cache", "spmm_rows_per_warp", "dec_splits",
                                                      "spmm_stages", "spmm_bins", "dec_rows",
@@ -25,7 +26,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-int32_t tuning(int idx) { return g_tuning[idx].load(std::memory_order_relaxed); }
+int32_t tuning(int idx) { return g_tuning[idx]; }
 
 }  // namespace gae
 
@@ -37,7 +38,7 @@ extern "C" int gae_set_tuning(const char *key, int32_t value) {
     if (key) {
         for (int i = 0; i < gae::T_COUNT; ++i)
             if (strcmp(key, gae::g_tuning_names[i]) == 0) {
-                gae::g_tuning[i].store(value);
+                gae::g_tuning[i] = value;
                 return GAE_OK;
             }
     }
@@ -47,6 +48,6 @@ extern "C" int gae_set_tuning(const char *key, int32_t value) {
 extern "C" int32_t gae_get_tuning(const char *key) {
     if (key)
         for (int i = 0; i < gae::T_COUNT; ++i)
-            if (strcmp(key, gae::g_tuning_names[i]) == 0) return gae::g_tuning[i].load();
+            if (strcmp(key, gae::g_tuning_names[i]) == 0) return gae::g_tuning[i];
     return -1;
 }

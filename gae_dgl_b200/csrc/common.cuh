@@ -23,7 +23,7 @@ enum TuningIdx {
     T_SPMM_BINS,         // 1 = use the plan's degree bins when present, 0 = single row pass
     T_DEC_ROWS,          // decoder dense pass: query rows per thread for d <= 16 (1 or 2)
     T_SPMM_SEG_ORDER,    // 1 = walk hub segments in the plan's seg_order (source-id order), 0 = row-major
-    T_SPMM_FUSED,        // experimental: 1 = all row classes + hub segments of the binned forward in one launch (spmm_fused.cu)
+    T_SPMM_FUSED,        // 1 = all row classes + hub segments of the binned forward in one launch (spmm_fused.cu), 0 = off, -1 = by size
     T_DEC_MMA,           // decoder dense pass, d <= 16: 1 = both GEMMs as split-precision TF32 MMAs (default), 0 = SIMT FFMA2
     T_COUNT
 };

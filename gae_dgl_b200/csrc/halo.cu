@@ -33,7 +33,11 @@ namespace gae {
 __host__ __device__ __forceinline__ int landed_off(int peer, int stage) { return peer * GAE_HALO_MAX_STAGES + stage; }
 __host__ __device__ __forceinline__ int consumed_off(int peer) { return GAE_HALO_MAX_WORLD * GAE_HALO_MAX_STAGES + peer; }
 constexpr int HALO_ERR_OFF = GAE_HALO_MAX_WORLD * GAE_HALO_MAX_STAGES + GAE_HALO_MAX_WORLD;
-static_assert(HALO_ERR_OFF + 1 <= GAE_HALO_FLAG_WORDS, "flag block too small");
+// timeline of the last call (%globaltimer ns of this GPU), for tools/halo_trace.py: push start, per stage
+// the time the push published it / the consumer began and ended waiting for it, and the release
+constexpr int HALO_TRACE_OFF = HALO_ERR_OFF + 1;
+constexpr int HALO_TRACE_WORDS = 2 + 3 * GAE_HALO_MAX_STAGES;
+static_assert(HALO_TRACE_OFF + HALO_TRACE_WORDS <= GAE_HALO_FLAG_WORDS, "flag block too small");
 
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
     uint64_t v;
@@ -80,37 +84,69 @@ struct PushArgs {
     int64_t stage_ptr[GAE_HALO_MAX_STAGES + 1];
 };
 
-// LPR lanes (a power of two) cover the d4 float4 of a row; U rows in flight per lane group.
+// LPR lanes (a power of two) cover the d4 float4 of a row.  A warp takes 32 consecutive entries of
+// the send list: every lane loads one entry's (src, peer, dst) -- one coalesced index load per 32
+// rows -- and the rows are then moved 32/LPR at a time, U of those steps in flight, the indices
+// handed around by shuffles.
 template <int LPR, int U>
 __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
+    __shared__ float *peer_base[GAE_HALO_MAX_WORLD];
     uint64_t *err = a.my_flags + HALO_ERR_OFF;
     // write-after-read: every consumer must have finished the previous SpMM on its halo region
-    if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank)
-        spin_until(a.my_flags + consumed_off(threadIdx.x), a.epoch - 1, a.timeout_ns, err);
+    if ((int)threadIdx.x < a.world) {
+        peer_base[threadIdx.x] = a.peer_x[threadIdx.x];
+        if ((int)threadIdx.x != a.rank) spin_until(a.my_flags + consumed_off(threadIdx.x), a.epoch - 1, a.timeout_ns, err);
+    }
     __syncthreads();
-    const int lane = threadIdx.x % LPR;
-    const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    const int64_t n_slots = (int64_t)gridDim.x * blockDim.x / LPR;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.my_flags[HALO_TRACE_OFF] = global_timer_ns();
+    constexpr int RPI = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int s = 0; s < a.n_stages; ++s) {
         const int64_t e0 = a.stage_ptr[s], e1 = a.stage_ptr[s + 1];
-        for (int64_t r = e0 + slot; r < e1; r += n_slots * U) {
-            int64_t src[U], dst[U];
-            int32_t peer[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t rr = min(r + u * n_slots, e1 - 1);
-                src[u] = __ldg(a.send_src + rr);
-                dst[u] = __ldg(a.send_dst + rr);
-                peer[u] = __ldg(a.send_peer + rr);
+        // the indices of the NEXT batch are loaded before the rows of the current one are moved
+        int64_t base = e0 + warp * 32;
+        int64_t nx_src = 0, nx_dst = 0;
+        int nx_peer = a.rank;
+        if (base + lane < e1) {
+            nx_src = __ldg(a.send_src + base + lane);
+            nx_dst = __ldg(a.send_dst + base + lane);
+            nx_peer = __ldg(a.send_peer + base + lane);
+        }
+        for (; base < e1; base += n_warps * 32) {
+            const int64_t my_src = nx_src, my_dst = nx_dst;
+            const int my_peer = nx_peer;
+            const int64_t nidx = base + n_warps * 32 + lane;
+            if (nidx < e1) {
+                nx_src = __ldg(a.send_src + nidx);
+                nx_dst = __ldg(a.send_dst + nidx);
+                nx_peer = __ldg(a.send_peer + nidx);
             }
-            for (int c = lane; c < a.d4; c += LPR) {
-                float4 v[U];
+            const int cnt = (int)min((int64_t)32, e1 - base);
+            for (int k = 0; k < cnt; k += RPI * U) {
+                const float4 *sp[U];
+                float4 *dp[U];
+                bool on[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4 *>(a.X + src[u] * a.ldx) + c);
+                for (int u = 0; u < U; ++u) {
+                    const int row = k + u * RPI + rsel;
+                    const int rr = min(row, cnt - 1);
+                    const int64_t src = __shfl_sync(0xffffffffu, my_src, rr);
+                    const int64_t dst = __shfl_sync(0xffffffffu, my_dst, rr);
+                    const int peer = __shfl_sync(0xffffffffu, my_peer, rr);
+                    on[u] = row < cnt;
+                    sp[u] = reinterpret_cast<const float4 *>(a.X + src * a.ldx);
+                    dp[u] = reinterpret_cast<float4 *>(peer_base[peer] + dst * a.ld_peer);
+                }
+                for (int c = sub; c < a.d4; c += LPR) {
+                    float4 v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (r + u * n_slots < e1)
-                        reinterpret_cast<float4 *>(a.peer_x[peer[u]] + dst[u] * a.ld_peer)[c] = v[u];
+                    for (int u = 0; u < U; ++u) v[u] = __ldg(sp[u] + c);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (on[u]) dp[u][c] = v[u];
+                }
             }
         }
         // stage s complete on this CTA; the last CTA to arrive publishes it to every peer
@@ -120,6 +156,7 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
             const unsigned old = atomicAdd(a.stage_done + s, 1u);
             if (old == gridDim.x - 1) {
                 a.stage_done[s] = 0;   // for the next launch (stream-ordered after this one)
+                a.my_flags[HALO_TRACE_OFF + 2 + 3 * s] = global_timer_ns();
                 __threadfence_system();
                 for (int q = 0; q < a.world; ++q)
                     if (q != a.rank) st_release_sys(a.peer_flags[q] + landed_off(a.rank, s), a.epoch);
@@ -131,11 +168,15 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
 __global__ void halo_wait_kernel(uint64_t *my_flags, int world, int rank, int stage, uint64_t epoch,
                                  uint64_t timeout_ns) {
     const int q = threadIdx.x;
+    if (q == 0) my_flags[HALO_TRACE_OFF + 2 + 3 * stage + 1] = global_timer_ns();
     if (q < world && q != rank) spin_until(my_flags + landed_off(q, stage), epoch, timeout_ns, my_flags + HALO_ERR_OFF);
+    __syncwarp();
+    if (q == 0) my_flags[HALO_TRACE_OFF + 2 + 3 * stage + 2] = global_timer_ns();
 }
 
 __global__ void halo_release_kernel(uint64_t *const *peer_flags, int world, int rank, uint64_t epoch) {
     const int q = threadIdx.x;
+    if (q == 0) peer_flags[rank][HALO_TRACE_OFF + 1] = global_timer_ns();
     __threadfence_system();
     if (q < world && q != rank) st_release_sys(peer_flags[q] + consumed_off(rank), epoch);
 }
@@ -175,19 +216,19 @@ extern "C" int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, 
     a.epoch = epoch; a.timeout_ns = timeout_of(ex);
     for (int s = 0; s <= ex->n_stages; ++s) a.stage_ptr[s] = ex->stage_ptr[s];
     int ctas = ex->push_ctas > 0 ? ex->push_ctas : 64;
-    int threads = ex->push_threads > 0 ? ex->push_threads : 512;
+    int threads = ex->push_threads > 0 ? ex->push_threads : 256;
     if (threads > 512) threads = 512;
     threads = (threads + 31) / 32 * 32;
     // a few dozen CTAs saturate NVLink; more would only take SMs from the row-block SpMMs running beside it
     int dev = 0, sms = 0;
     GAE_CUDA(cudaGetDevice(&dev));
     GAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (ctas > sms) ctas = sms;
+    if (ctas > 2 * sms) ctas = 2 * sms;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.d4 <= 4) halo_push_kernel<4, 4><<<ctas, threads, 0, st>>>(a);
+    if (a.d4 <= 4) halo_push_kernel<4, 2><<<ctas, threads, 0, st>>>(a);
     else if (a.d4 <= 8) halo_push_kernel<8, 4><<<ctas, threads, 0, st>>>(a);
-    else if (a.d4 <= 16) halo_push_kernel<16, 4><<<ctas, threads, 0, st>>>(a);
-    else halo_push_kernel<32, 4><<<ctas, threads, 0, st>>>(a);
+    else if (a.d4 <= 16) halo_push_kernel<16, 8><<<ctas, threads, 0, st>>>(a);
+    else halo_push_kernel<32, 8><<<ctas, threads, 0, st>>>(a);
     GAE_LAUNCH_CHECK();
     return GAE_OK;
 }
@@ -212,40 +253,52 @@ extern "C" int gae_halo_release_f32(const gae_halo_exchange_t *ex, uint64_t epoc
 }
 
 extern "C" int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_block_t *blocks, float *Y, int64_t ldy,
-                                 uint64_t epoch, void *compute_stream, void *comm_stream) {
+                                 uint64_t epoch, void *compute_stream, void *comm_stream, void *aux_stream) {
     int rc = check_exchange(ex);
     if (rc) return rc;
     GAE_CHECK_ARG(blocks && Y && ldy >= ex->d, "null blocks / output");
     GAE_CHECK_ARG(epoch >= 1, "epochs count from 1");
-    cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
+    cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream, as = (cudaStream_t)aux_stream;
     GAE_CHECK_ARG(ex->world == 1 || cs != ms, "the exchange needs its own stream");
-    cudaEvent_t ready = nullptr, pushed = nullptr;
-    if (ex->world > 1) {
-        // the push may start once everything queued on the compute stream (the producer of the
-        // local rows) is done; it then runs ahead of the row blocks
-        GAE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        GAE_CUDA(cudaEventCreateWithFlags(&pushed, cudaEventDisableTiming));
-        GAE_CUDA(cudaEventRecord(ready, cs));
-        GAE_CUDA(cudaStreamWaitEvent(ms, ready, 0));
-        rc = gae_halo_push_f32(ex, epoch, comm_stream);
-        if (rc == GAE_OK) {
-            GAE_CUDA(cudaEventRecord(pushed, ms));
-        }
+    const bool two = aux_stream != nullptr && as != cs && as != ms && ex->n_stages > 1;
+    for (int s = 1; s < ex->n_stages && two; ++s)
+        GAE_CHECK_ARG(!blocks[s].partial_ws || blocks[s].partial_ws != blocks[s - 1].partial_ws,
+                      "consecutive row blocks run concurrently: they need separate segment workspaces");
+    cudaEvent_t ready = nullptr, pushed = nullptr, aux_done = nullptr;
+    GAE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    GAE_CUDA(cudaEventCreateWithFlags(&pushed, cudaEventDisableTiming));
+    GAE_CUDA(cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming));
+    // the push may start once everything queued on the compute stream (the producer of the local
+    // rows) is done; it then runs ahead of the row blocks
+    rc = (int)cudaEventRecord(ready, cs);
+    if (rc == GAE_OK && ex->world > 1) {
+        rc = (int)cudaStreamWaitEvent(ms, ready, 0);
+        if (rc == GAE_OK) rc = gae_halo_push_f32(ex, epoch, comm_stream);
+        if (rc == GAE_OK) rc = (int)cudaEventRecord(pushed, ms);
     }
+    if (rc == GAE_OK && two) rc = (int)cudaStreamWaitEvent(as, ready, 0);
+    // Row blocks alternate between the compute stream and the auxiliary stream: block s+1 depends on
+    // its own flags only (its rows of Y and its segment workspace are private), so its first CTAs
+    // fill the SMs that the tail of block s leaves idle instead of waiting behind a kernel boundary.
     for (int s = 0; s < ex->n_stages && rc == GAE_OK; ++s) {
-        rc = gae_halo_wait_f32(ex, s, epoch, compute_stream);
+        void *st = (two && (s & 1)) ? aux_stream : compute_stream;
+        rc = gae_halo_wait_f32(ex, s, epoch, st);
         const gae_halo_block_t &b = blocks[s];
         if (rc == GAE_OK && b.n_rows > 0)
             rc = gae_spmm_csr_f32(b.rowptr, b.col, nullptr, ex->x_local, ex->ld, Y + b.row0 * ldy, ldy, b.n_rows, ex->d,
-                                  b.plan, b.partial_ws, 0, compute_stream);
+                                  b.plan, b.partial_ws, 0, st);
+    }
+    if (rc == GAE_OK && two) {
+        rc = (int)cudaEventRecord(aux_done, as);
+        if (rc == GAE_OK) rc = (int)cudaStreamWaitEvent(cs, aux_done, 0);
     }
     if (rc == GAE_OK) rc = gae_halo_release_f32(ex, epoch, compute_stream);
-    if (ex->world > 1) {
-        // callers may overwrite their local rows after this op: the push must have read them
-        if (rc == GAE_OK) cudaStreamWaitEvent(cs, pushed, 0);
-        cudaEventDestroy(ready);
-        cudaEventDestroy(pushed);
-    }
+    // callers may overwrite their local rows after this op: the push must have read them
+    if (rc == GAE_OK && ex->world > 1) rc = (int)cudaStreamWaitEvent(cs, pushed, 0);
+    cudaEventDestroy(ready);
+    cudaEventDestroy(pushed);
+    cudaEventDestroy(aux_done);
+    if (rc > 0) set_error("gae_halo_spmm_f32: CUDA error %d (%s)", rc, cudaGetErrorString((cudaError_t)rc));
     return rc;
 }
 

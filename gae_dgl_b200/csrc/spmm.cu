@@ -298,6 +298,9 @@ static cudaError_t launch_vec(const SpmmArgs &a, int rows_per_warp, int unroll, 
     return launch_shape<32, 1, SEG>(a, unroll, cache, block, st);
 }
 
+// rows up to which the automatic setting takes the single-launch form (profiles/r02_fused_sweep.log)
+constexpr int64_t FUSED_AUTO_MAX_ROWS = (int64_t)1 << 40;
+
 cudaError_t spmm_stream_launch(const StreamArgs &a, int d, bool seg, int stages, int mode, cudaStream_t st);
 bool spmm_fused_launch(const int64_t *rowptr, const int32_t *col, const float *X, int64_t ldx, float *Y, int64_t ldy,
                        int32_t d, const gae_hub_plan_t *plan, float *partial_ws, int64_t ldp, bool seg_order,
@@ -367,8 +370,10 @@ extern "C" int gae_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const
     }
     const bool binned = plan && plan->mid_rows && plan->short_rows && plan->empty_rows && d % 4 == 0 && d <= 64 &&
                         plan->short_max == 4 && !vals && tuning(T_SPMM_BINS) != 0;
-    if (binned && !accumulate && cache == 0 && tuning(T_SPMM_FUSED) != 0) {
-        // experimental: all row classes and the hub segments in one launch (spmm_fused.cu)
+    // single-launch form (spmm_fused.cu): 1 = on, 0 = off, -1 = by size (FUSED_AUTO_MAX_ROWS)
+    const int fused_knob = tuning(T_SPMM_FUSED);
+    const bool fused = fused_knob > 0 || (fused_knob < 0 && n_rows <= FUSED_AUTO_MAX_ROWS);
+    if (binned && !accumulate && cache == 0 && fused) {
         const int64_t ldp = (int64_t)((d + 3) / 4) * 4;
         cudaError_t e = cudaSuccess;
         if (spmm_fused_launch(rowptr, col, X, ldx, Y, ldy, d, plan, partial_ws, ldp, tuning(T_SPMM_SEG_ORDER) != 0, st, &e)) {

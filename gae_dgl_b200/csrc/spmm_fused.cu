@@ -1,18 +1,17 @@
-// EXPERIMENTAL (tuning "spmm_fused" = 1, default 0; not measured yet): the degree-binned forward of
-// spmm.cu as ONE launch whose blocks take different roles.
-//
-// ncu on C4 (profiles/r01_spmm_final_ncu_full_summary.csv): the mid-row kernel (rows of 5..512 edges,
-// 42 M edges) runs 1.05 ms latency-bound -- 37 of 48 warps resident, 77 % of the warp cycles waiting
-// on gathers, L2->SM path 43 % busy -- while the hub-segment kernel (56 M edges) moves 12.3 GB in
-// 0.83 ms, and the zero-fill / short-row kernels add two more launches with their own ramps and
-// tails.  Launched one after the other they cannot share an SM: the block scheduler drains one grid
-// before it starts the next.  Here hub-segment blocks and mid-row blocks are interleaved over
-// blockIdx in proportion to their counts (integer Bresenham), so every SM holds bandwidth-efficient
-// segment warps and latency-bound row warps at the same time; short-row and zero-fill blocks follow
-// at the tail of the same grid.  The per-row / per-segment summation is the routine of
+// Single-launch form of the degree-binned forward of spmm.cu (tuning "spmm_fused": 1 = on, 0 = off,
+// -1 = automatic by size): the blocks of ONE grid take the four roles one after the other --
+// hub segments (source order), mid rows (degree order), short rows, zero fill -- instead of four
+// launches with their ramps and tails.  The per-row / per-segment summation is the routine of
 // spmm_vec_kernel (edge e to lane group e mod GPR, U gathers in flight, xor-shuffle tree) and of
-// spmm_short_rows_kernel: results are bit-identical to the separate launches.  The ordered hub
-// reduce stays a second (tiny) launch.
+// spmm_short_rows_kernel: results are bit-identical to the separate launches (tested).  The ordered
+// hub reduce stays a second (tiny) launch.
+//
+// Measured (B200, profiles/r02_round2_checks.log): an earlier form that INTERLEAVED hub-segment and
+// mid-row blocks over blockIdx (so that every SM held both kinds at once) was 10 % slower than the
+// separate launches on C4 (2.29 vs 2.09 ms; the random mid-row gathers evict the L2-resident source
+// band the ordered segments live on) and 25 % faster on 1.5 M-edge graphs (0.056 vs 0.074 ms,
+// launch-bound).  Roles are therefore sequential in blockIdx here.  The partitioned multi-GPU
+// operator (halo.cu) runs one such launch per row block.
 #include "common.cuh"
 
 namespace gae {
@@ -37,7 +36,7 @@ struct FusedArgs {
     const int32_t *seg_row;
     const int32_t *seg_order;
     int64_t n_mid, n_short, n_empty, n_seg;
-    // block ranges: [0, nb_hub + nb_mid) interleaved hub/mid, then nb_short, then nb_zero
+    // block ranges: nb_hub hub-segment blocks, then nb_mid, nb_short, nb_zero
     int64_t nb_hub, nb_mid, nb_short, nb_zero;
 };
 
@@ -95,9 +94,8 @@ __global__ void __launch_bounds__(fused::BLOCK, 24) spmm_fused_kernel(const Fuse
     const int64_t b = blockIdx.x;
     const int64_t n_hm = a.nb_hub + a.nb_mid;
     if (b < n_hm) {
-        // Bresenham split of [0, n_hm) into nb_hub hub blocks and nb_mid mid blocks, evenly interleaved
-        const int64_t hub_before = (b * a.nb_hub) / n_hm;
-        const bool is_hub = ((b + 1) * a.nb_hub) / n_hm > hub_before;
+        const bool is_hub = b < a.nb_hub;
+        const int64_t hub_before = is_hub ? b : a.nb_hub;
         if (is_hub) {
             const int64_t item = hub_before * 2 + warp;
             if (item >= a.n_seg) return;

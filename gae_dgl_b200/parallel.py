@@ -297,7 +297,7 @@ class HaloSpMM:
     exchange = "halo"
 
     def __init__(self, hp: HaloPlan, d: int, n_stages: int = DEFAULT_STAGES, group=None, push_ctas: int = 0,
-                 push_threads: int = 0, timeout_ms: int = 0):
+                 push_threads: int = 0, timeout_ms: int = 0, two_streams: bool = True):
         if d % 4 != 0:
             raise GaeError("the halo exchange needs 16-byte rows (d a multiple of 4)")
         self.hp, self.d, self.group = hp, d, group
@@ -305,10 +305,13 @@ class HaloSpMM:
         self.sp = sp = build_stage_plan(hp, n_stages, group)
         self.X_ext = ops.alloc_rows(hp.n_local + hp.n_halo, d, dev)
         self.Y = ops.alloc_rows(hp.n_local, d, dev)
-        n_seg = max([p.n_seg for p in sp.sub_plan if p is not None] + [0])
-        self.ws = torch.empty((max(n_seg, 1), ops.round_up4(d)), dtype=torch.float32, device=dev)
+        # one segment workspace, a private slice per row block (consecutive blocks overlap in time)
+        seg_counts = [p.n_seg if p is not None else 0 for p in sp.sub_plan]
+        self.ws = torch.empty((max(sum(seg_counts), 1), ops.round_up4(d)), dtype=torch.float32, device=dev)
+        seg_first = [sum(seg_counts[:s]) for s in range(sp.n_stages)]
         self.epoch = 0
         self._comm = torch.cuda.Stream(device=dev)
+        self._aux = torch.cuda.Stream(device=dev) if two_streams else None
         ex = HaloExchangeStruct()
         ex.world, ex.rank, ex.n_stages, ex.d = hp.world, hp.rank, sp.n_stages, d
         ex.ld = self.X_ext.stride(0)
@@ -340,7 +343,7 @@ class HaloSpMM:
             p = sp.sub_plan[s]
             if p is not None and (p.n_seg > 0 or p.bins is not None):
                 blocks[s].plan = ctypes.addressof(p.struct)
-            blocks[s].partial_ws = self.ws.data_ptr()
+            blocks[s].partial_ws = self.ws[seg_first[s]:].data_ptr() if seg_counts[s] else None
         self._blocks = blocks
         if hp.world > 1:
             torch.cuda.synchronize(dev)
@@ -357,9 +360,25 @@ class HaloSpMM:
     def __call__(self) -> torch.Tensor:
         self.epoch += 1
         rc = _lib.load().gae_halo_spmm_f32(ctypes.byref(self._ex), self._blocks, ctypes.c_void_p(self.Y.data_ptr()),
-                                           self.Y.stride(0), self.epoch, ops._stream(), self._comm.cuda_stream)
+                                           self.Y.stride(0), self.epoch, ops._stream(), self._comm.cuda_stream,
+                                           self._aux.cuda_stream if self._aux is not None else None)
         _lib.check(rc, "gae_halo_spmm_f32")
         return self.Y
+
+    def trace(self) -> dict:
+        """Timeline of the last call in microseconds after the push started (synchronises): when the push
+        published each stage to the peers, and when the consumer began / stopped waiting for each stage."""
+        torch.cuda.synchronize(self.flags.device)
+        off = 16 * 32 + 16 + 1                       # HALO_TRACE_OFF
+        w = self.flags.cpu().numpy().astype(np.int64)
+        t0 = int(w[off])
+        us = lambda x: round((int(x) - t0) / 1e3, 1)  # noqa: E731
+        n = self.sp.n_stages
+        return {"published_us": [us(w[off + 2 + 3 * s]) for s in range(n)],
+                "wait_begin_us": [us(w[off + 2 + 3 * s + 1]) for s in range(n)],
+                "wait_end_us": [us(w[off + 2 + 3 * s + 2]) for s in range(n)],
+                "release_us": us(w[off + 1]),
+                "stage_rows": [int(self.sp.stage_ptr[s + 1] - self.sp.stage_ptr[s]) for s in range(n)]}
 
     def check(self) -> None:
         """Synchronous: raise if any flag wait of this operator timed out."""
@@ -568,7 +587,8 @@ class RmatPartition:
 
 
 def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device, exchange: str = "auto",
-                         group=None, stages: int = DEFAULT_STAGES, push_ctas: int = 0) -> RmatPartition:
+                         group=None, stages: int = DEFAULT_STAGES, push_ctas: int = 0,
+                         two_streams: bool = True) -> RmatPartition:
     """Distributed R-MAT workload: every rank draws 1/P of the edge stream, edges are routed to the owner
     of their row, and the forward (rows = dst) and backward (rows = src) partitioned operators are built.
     exchange: "halo" (staged one-sided push with device flags, overlapped with `stages` row blocks),
@@ -597,8 +617,8 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
 
     def make_ops(mode):
         if mode == "halo":
-            return (HaloSpMM(hp_f, d, stages, group, push_ctas=push_ctas),
-                    HaloSpMM(hp_b, d, stages, group, push_ctas=push_ctas))
+            return (HaloSpMM(hp_f, d, stages, group, push_ctas=push_ctas, two_streams=two_streams),
+                    HaloSpMM(hp_b, d, stages, group, push_ctas=push_ctas, two_streams=two_streams))
         return PartitionedSpMM(hp_f, d, mode, group), PartitionedSpMM(hp_b, d, mode, group)
 
     if requested == "auto":

@@ -113,6 +113,16 @@ def hashed_normal(n_rows: int, d: int, seed: int, device="cpu", first_row: int =
     return out
 
 
+def hashed_normal_rows(ids: torch.Tensor, d: int, seed: int) -> torch.Tensor:
+    """Rows `ids` (int64, any order) of the matrix hashed_normal(n, d, seed) without building it."""
+    idx = ids.to(torch.int64)[:, None] * d + torch.arange(d, dtype=torch.int64, device=ids.device)[None, :]
+    h = splitmix64(idx + _s64(splitmix_scalar(seed + 77)))
+    s = torch.zeros(idx.shape, dtype=torch.float32, device=ids.device)
+    for q in range(4):
+        s += (_lsr(h, 16 * q) & 0xFFFF).to(torch.float32)
+    return (s - 2.0 * 65535.0) / float(np.sqrt(4.0 * (65536.0 ** 2 - 1.0) / 12.0))
+
+
 # ---- Planetoid-shaped citation graphs ------------------------------------------------------------
 
 PLANETOID_SHAPES = {

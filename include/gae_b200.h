@@ -269,9 +269,12 @@ int gae_ipc_close_handle(void *dev_ptr);
  *                         and publishes landed[rank][stage] = epoch to every peer after each stage;
  *   gae_halo_wait_f32     one-warp kernel: acquires landed[q][stage] >= epoch from all peers q;
  *   gae_halo_release_f32  publishes consumed[rank] = epoch to every peer (my halo may be overwritten);
- *   gae_halo_spmm_f32     the whole operator Y = (A X)[my rows]: push on comm_stream, and on
- *                         compute_stream for s = 0..n_stages-1 { wait(s); SpMM of row block s } + release,
- *                         so the transfer of later stages overlaps the aggregation of earlier ones.
+ *   gae_halo_spmm_f32     the whole operator Y = (A X)[my rows]: push on comm_stream, and for
+ *                         s = 0..n_stages-1 { wait(s); SpMM of row block s } + release, so the transfer
+ *                         of later stages overlaps the aggregation of earlier ones.  Row blocks alternate
+ *                         between compute_stream and aux_stream (NULL = all on compute_stream; consecutive
+ *                         blocks then need no separate partial_ws) so that the tail of one block overlaps
+ *                         the head of the next; everything is joined back into compute_stream.
  * `epoch` counts the calls on one operator from 1.  Flag waits are bounded by timeout_ms (default 10 s):
  * on expiry an error word is set and the kernel falls through -- gae_halo_status() reports it -- so a
  * protocol fault gives a wrong, reported result and never a hung GPU.  Replaces nothing in the reference
@@ -292,7 +295,7 @@ typedef struct gae_halo_exchange_t {
     const int64_t *stage_ptr;     /* HOST [n_stages+1]: entry range of each stage                       */
     uint32_t *stage_done;         /* DEVICE [n_stages]: zero-initialised arrival counters (scratch)     */
     int32_t push_ctas;            /* 0 = default (64)                                                   */
-    int32_t push_threads;         /* 0 = default (512)                                                  */
+    int32_t push_threads;         /* 0 = default (256)                                                  */
     int32_t timeout_ms;           /* 0 = default (10000)                                                */
 } gae_halo_exchange_t;
 typedef struct gae_halo_block_t {
@@ -306,7 +309,8 @@ int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *strea
 int gae_halo_wait_f32(const gae_halo_exchange_t *ex, int32_t stage, uint64_t epoch, void *stream);
 int gae_halo_release_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
 int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_block_t *blocks /* HOST [n_stages] */,
-                      float *Y, int64_t ldy, uint64_t epoch, void *compute_stream, void *comm_stream);
+                      float *Y, int64_t ldy, uint64_t epoch, void *compute_stream, void *comm_stream,
+                      void *aux_stream);
 /* Synchronous: copies the error word back; GAE_ERR_TIMEOUT if any flag wait expired since start. */
 int gae_halo_status(const gae_halo_exchange_t *ex, int64_t *timeouts);
 
