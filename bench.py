@@ -57,6 +57,9 @@ def parse_args():
     p.add_argument("--stages", type=int, default=8,
                    help="N > 1, exchange 'halo': stages of the one-sided push overlapped with that many row-block SpMMs")
     p.add_argument("--push-ctas", type=int, default=0, help="N > 1, exchange 'halo': CTAs of the push kernel (0 = 64)")
+    p.add_argument("--halo-kind", type=str, default="classes", choices=["classes", "blocks"],
+                   help="exchange 'halo': stages = popularity classes of the halo rows (default) or row blocks")
+    p.add_argument("--hot", type=str, default="8", help="halo-kind classes: descending reference-count thresholds, e.g. 32,4")
     return p.parse_args()
 
 
@@ -489,7 +492,8 @@ def run_ours(args):
     else:
         from gae_dgl_b200 import parallel
         part = parallel.build_rmat_partition(scale, total_edges, seed=1, d=D_FEAT, device=dev,
-                                             exchange=args.exchange, stages=args.stages, push_ctas=args.push_ctas)
+                                             exchange=args.exchange, stages=args.stages, push_ctas=args.push_ctas,
+                                             kind=args.halo_kind, thresholds=tuple(int(x) for x in args.hot.split(",")))
         fwd, bwd = part.fwd, part.bwd
         local_edges, local_rows = part.local_edges, part.local_rows
         exchange_desc = part.exchange_desc

@@ -68,6 +68,7 @@ class HaloBlockStruct(Structure):
     _fields_ = [
         ("row0", c_int64), ("n_rows", c_int64),
         ("rowptr", c_void_p), ("col", c_void_p), ("plan", c_void_p), ("partial_ws", c_void_p),
+        ("accumulate", c_int32),
     ]
 
 
@@ -133,8 +134,8 @@ SIGNATURES = {
     "gae_halo_plan_count_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, POINTER(c_int64), c_void_p]),
     "gae_halo_plan_fill_host": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "gae_halo_stage_tags_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
-    "gae_halo_push_lists_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
-                                         c_void_p, c_void_p]),
+    "gae_halo_push_lists_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "gae_adam_step_f32": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_int64), c_float, c_float, c_float, c_float, c_int64, c_void_p]),
 }

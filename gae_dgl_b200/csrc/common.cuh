@@ -25,6 +25,8 @@ enum TuningIdx {
     T_SPMM_SEG_ORDER,    // 1 = walk hub segments in the plan's seg_order (source-id order), 0 = row-major
     T_SPMM_FUSED,        // 1 = all row classes + hub segments of the binned forward in one launch (spmm_fused.cu), 0 = off, -1 = by size
     T_DEC_MMA,           // decoder dense pass, d <= 16: 1 = both GEMMs as split-precision TF32 MMAs (default), 0 = SIMT FFMA2
+    T_PUSH_UNROLL,       // halo push kernel: row steps in flight per lane group (4 or 8; registers 55 / 106)
+    T_PUSH_STREAM_LD,    // halo push kernel: 1 = read the local rows with evict-first loads (ld.global.cs)
     T_COUNT
 };
 

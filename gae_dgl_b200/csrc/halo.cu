@@ -88,7 +88,7 @@ struct PushArgs {
 // the send list: every lane loads one entry's (src, peer, dst) -- one coalesced index load per 32
 // rows -- and the rows are then moved 32/LPR at a time, U of those steps in flight, the indices
 // handed around by shuffles.
-template <int LPR, int U>
+template <int LPR, int U, bool STREAM>
 __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
     __shared__ float *peer_base[GAE_HALO_MAX_WORLD];
     uint64_t *err = a.my_flags + HALO_ERR_OFF;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
                 for (int c = sub; c < a.d4; c += LPR) {
                     float4 v[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) v[u] = __ldg(sp[u] + c);
+                    for (int u = 0; u < U; ++u) v[u] = STREAM ? __ldcs(sp[u] + c) : __ldg(sp[u] + c);
 #pragma unroll
                     for (int u = 0; u < U; ++u)
                         if (on[u]) dp[u][c] = v[u];
@@ -225,10 +225,17 @@ extern "C" int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, 
     GAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (ctas > 2 * sms) ctas = 2 * sms;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.d4 <= 4) halo_push_kernel<4, 2><<<ctas, threads, 0, st>>>(a);
-    else if (a.d4 <= 8) halo_push_kernel<8, 4><<<ctas, threads, 0, st>>>(a);
-    else if (a.d4 <= 16) halo_push_kernel<16, 8><<<ctas, threads, 0, st>>>(a);
-    else halo_push_kernel<32, 8><<<ctas, threads, 0, st>>>(a);
+    const bool u8 = tuning(T_PUSH_UNROLL) >= 8, cs_ld = tuning(T_PUSH_STREAM_LD) != 0;
+#define GAE_PUSH(LPR, U)                                                              \
+    do {                                                                              \
+        if (cs_ld) halo_push_kernel<LPR, U, true><<<ctas, threads, 0, st>>>(a);       \
+        else halo_push_kernel<LPR, U, false><<<ctas, threads, 0, st>>>(a);            \
+    } while (0)
+    if (a.d4 <= 4) GAE_PUSH(4, 2);
+    else if (a.d4 <= 8) GAE_PUSH(8, 4);
+    else if (a.d4 <= 16) { if (u8) GAE_PUSH(16, 8); else GAE_PUSH(16, 4); }
+    else { if (u8) GAE_PUSH(32, 8); else GAE_PUSH(32, 4); }
+#undef GAE_PUSH
     GAE_LAUNCH_CHECK();
     return GAE_OK;
 }
@@ -260,7 +267,8 @@ extern "C" int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_b
     GAE_CHECK_ARG(epoch >= 1, "epochs count from 1");
     cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream, as = (cudaStream_t)aux_stream;
     GAE_CHECK_ARG(ex->world == 1 || cs != ms, "the exchange needs its own stream");
-    const bool two = aux_stream != nullptr && as != cs && as != ms && ex->n_stages > 1;
+    bool two = aux_stream != nullptr && as != cs && as != ms && ex->n_stages > 1;
+    for (int s = 0; s < ex->n_stages; ++s) two = two && !blocks[s].accumulate;   // passes that add into Y are ordered
     for (int s = 1; s < ex->n_stages && two; ++s)
         GAE_CHECK_ARG(!blocks[s].partial_ws || blocks[s].partial_ws != blocks[s - 1].partial_ws,
                       "consecutive row blocks run concurrently: they need separate segment workspaces");
@@ -286,7 +294,7 @@ extern "C" int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_b
         const gae_halo_block_t &b = blocks[s];
         if (rc == GAE_OK && b.n_rows > 0)
             rc = gae_spmm_csr_f32(b.rowptr, b.col, nullptr, ex->x_local, ex->ld, Y + b.row0 * ldy, ldy, b.n_rows, ex->d,
-                                  b.plan, b.partial_ws, 0, st);
+                                  b.plan, b.partial_ws, b.accumulate, st);
     }
     if (rc == GAE_OK && two) {
         rc = (int)cudaEventRecord(aux_done, as);
@@ -418,10 +426,12 @@ extern "C" int gae_halo_stage_tags_host(const int64_t *rowptr, const int32_t *co
     return GAE_OK;
 }
 
-extern "C" int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *send_stage, const int64_t *send_counts,
-                                        const int64_t *dst_base, int32_t world, int32_t n_stages, int64_t *out_src,
-                                        int32_t *out_peer, int64_t *out_dst, int64_t *stage_ptr) {
-    GAE_CHECK_ARG(send_counts && dst_base && stage_ptr && world >= 1 && world <= GAE_HALO_MAX_WORLD, "bad arguments");
+extern "C" int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *send_stage, const int64_t *send_dst,
+                                        const int64_t *send_counts, const int64_t *dst_base, int32_t world,
+                                        int32_t n_stages, int64_t *out_src, int32_t *out_peer, int64_t *out_dst,
+                                        int64_t *stage_ptr) {
+    GAE_CHECK_ARG(send_counts && (dst_base || send_dst) && stage_ptr && world >= 1 && world <= GAE_HALO_MAX_WORLD,
+                  "bad arguments");
     GAE_CHECK_ARG(n_stages >= 1 && n_stages <= GAE_HALO_MAX_STAGES, "1 <= n_stages <= GAE_HALO_MAX_STAGES");
     int64_t m = 0;
     std::vector<int64_t> first(world + 1, 0);
@@ -464,7 +474,7 @@ extern "C" int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *
                     const int64_t j = bucket[(size_t)(start[(size_t)s * world + q] + k)];
                     out_src[o] = send_idx[j];
                     out_peer[o] = q;
-                    out_dst[o] = dst_base[q] + (j - first[q]);
+                    out_dst[o] = send_dst ? send_dst[j] : dst_base[q] + (j - first[q]);
                     ++o;
                 }
     }

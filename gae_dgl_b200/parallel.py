@@ -139,12 +139,20 @@ def build_halo_plan(src: torch.Tensor, dst: torch.Tensor, n_global: int, rank: i
 
 @dataclass
 class StagePlan:
+    """Stages of the exchange and the SpMM pieces that consume them.  kind "blocks": stage s = the halo rows
+    first read by row block s, piece s = the rows of that block over all their edges.  kind "classes":
+    stage s = the halo rows of popularity class s (the buffer keeps them in that order), piece s = ALL rows
+    over the edges whose source is in class s (local sources count as class 0), added into Y for s > 0."""
+    kind: str
     n_stages: int
-    row_bounds: List[int]                 # local row blocks, balanced by edge count; len = n_stages + 1
-    sub_rowptr: List[torch.Tensor]        # per block: rowptr rebased to 0
-    sub_col: List[torch.Tensor]           # per block: view into the local CSR's col array
+    row_bounds: List[int]                 # kind "blocks": local row blocks; kind "classes": [0, n_local]
+    piece_rows: List[tuple]               # per piece: (row0, n_rows)
+    sub_rowptr: List[torch.Tensor]        # per piece: rowptr rebased to 0
+    sub_col: List[torch.Tensor]           # per piece: columns in the [local | halo] buffer
     sub_plan: List[Optional[ops.HubPlan]]
-    halo_stage: torch.Tensor              # int32 [n_halo] (host): first block that reads each halo row
+    accumulate: List[bool]
+    halo_stage: torch.Tensor              # int32 [n_halo] (host): stage of each halo row (HaloPlan.halo_ids order)
+    halo_pos: torch.Tensor                # int64 [n_halo] (host): its row in my [local | halo] buffer
     send_stage: torch.Tensor              # int32 [S] (host): stage of every entry of HaloPlan.send_idx
     push_src: torch.Tensor                # int64 [S]: local rows to send, sorted by stage, peers interleaved
     push_peer: torch.Tensor               # int32 [S]
@@ -167,13 +175,42 @@ def edge_balanced_bounds(rowptr: np.ndarray, n_blocks: int) -> List[int]:
     return bounds
 
 
-def build_stage_plan(hp: HaloPlan, n_stages: int, group=None, seg_len: int = ops.DEFAULT_SEG_LEN) -> StagePlan:
-    """Cut the rank's rows into `n_stages` edge-balanced blocks, tag every halo row with the first block
-    that reads it (gae_halo_stage_tags_host), tell the owners, and build the staged send lists
-    (gae_halo_push_lists_host)."""
+def _send_lists(hp: HaloPlan, halo_stage: np.ndarray, halo_pos: np.ndarray, n_stages: int, group):
+    """Tell every owner the stage and the destination row of each row it sends me (same order as the request
+    lists), then build my own staged, peer-interleaved send lists (gae_halo_push_lists_host)."""
     lib = _lib.load()
     dev = hp.rowptr.device
-    world, rank = hp.world, hp.rank
+    m = int(hp.send_idx.numel())
+    send_stage = torch.empty(m, dtype=torch.int32, device=dev)
+    all_to_all_v(send_stage, torch.from_numpy(halo_stage).to(dev), hp.send_counts, hp.recv_counts, group)
+    send_dst = torch.empty(m, dtype=torch.int64, device=dev)
+    all_to_all_v(send_dst, torch.from_numpy(halo_pos).to(dev), hp.send_counts, hp.recv_counts, group)
+    send_idx = np.ascontiguousarray(hp.send_idx.cpu().numpy(), dtype=np.int64)
+    sst = np.ascontiguousarray(send_stage.cpu().numpy(), dtype=np.int32)
+    sdst = np.ascontiguousarray(send_dst.cpu().numpy(), dtype=np.int64)
+    sc = np.asarray(hp.send_counts, dtype=np.int64)
+    o_src, o_peer, o_dst = (np.zeros(max(m, 1), dtype=np.int64), np.zeros(max(m, 1), dtype=np.int32),
+                            np.zeros(max(m, 1), dtype=np.int64))
+    stage_ptr = np.zeros(n_stages + 1, dtype=np.int64)
+    _lib.check(lib.gae_halo_push_lists_host(_np_ptr(send_idx), _np_ptr(sst), _np_ptr(sdst), _np_ptr(sc), None, hp.world,
+                                            n_stages, _np_ptr(o_src), _np_ptr(o_peer), _np_ptr(o_dst), _np_ptr(stage_ptr)),
+               "gae_halo_push_lists_host")
+    return (torch.from_numpy(sst.copy()), torch.from_numpy(o_src[:m]).to(dev), torch.from_numpy(o_peer[:m]).to(dev),
+            torch.from_numpy(o_dst[:m]).to(dev), stage_ptr)
+
+
+def _piece_plan(rowptr: torch.Tensor, col: torch.Tensor, seg_len: int) -> Optional[ops.HubPlan]:
+    if not rowptr.is_cuda or rowptr.numel() <= 1:
+        return None
+    plan = ops.build_hub_plan(rowptr, seg_len)
+    ops.order_segments_by_source(plan, rowptr, col)
+    return plan
+
+
+def build_stage_plan(hp: HaloPlan, n_stages: int, group=None, seg_len: int = ops.DEFAULT_SEG_LEN) -> StagePlan:
+    """Row-block stages: cut the rank's rows into `n_stages` edge-balanced blocks and tag every halo row with
+    the first block that reads it (gae_halo_stage_tags_host).  The halo keeps the HaloPlan's layout."""
+    lib = _lib.load()
     n_stages = max(1, min(int(n_stages), 32))
     rp = hp.rowptr.cpu().numpy()
     cl = hp.col.cpu().numpy()
@@ -184,26 +221,8 @@ def build_stage_plan(hp: HaloPlan, n_stages: int, group=None, seg_len: int = ops
     _lib.check(lib.gae_halo_stage_tags_host(_np_ptr(rp), _np_ptr(cl), hp.n_local, hp.n_halo, _np_ptr(rb), n_stages,
                                             _np_ptr(halo_stage)), "gae_halo_stage_tags_host")
     halo_stage = halo_stage[:hp.n_halo]
-    # tell every owner the stage of each row it sends me (same order as the request lists)
-    hs = torch.from_numpy(halo_stage).to(dev)
-    send_stage = torch.empty(int(hp.send_idx.numel()), dtype=torch.int32, device=dev)
-    all_to_all_v(send_stage, hs, hp.send_counts, hp.recv_counts, group)
-    # where my rows land in each peer's buffer: peer q keeps the rows owned by rank r at halo offset cuts_q[r]
-    cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
-    cuts[1:] = torch.cumsum(torch.tensor(hp.recv_counts, dtype=torch.int64, device=dev), 0)
-    mine_at_peer = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_to_all_single(mine_at_peer, (cuts[:-1] + hp.n_local).contiguous(), group=group)
-    m = int(hp.send_idx.numel())
-    send_idx = np.ascontiguousarray(hp.send_idx.cpu().numpy(), dtype=np.int64)
-    sst = np.ascontiguousarray(send_stage.cpu().numpy(), dtype=np.int32)
-    sc = np.asarray(hp.send_counts, dtype=np.int64)
-    base = np.ascontiguousarray(mine_at_peer.cpu().numpy(), dtype=np.int64)
-    o_src, o_peer, o_dst = (np.zeros(max(m, 1), dtype=np.int64), np.zeros(max(m, 1), dtype=np.int32),
-                            np.zeros(max(m, 1), dtype=np.int64))
-    stage_ptr = np.zeros(n_stages + 1, dtype=np.int64)
-    _lib.check(lib.gae_halo_push_lists_host(_np_ptr(send_idx), _np_ptr(sst), _np_ptr(sc), _np_ptr(base), world, n_stages,
-                                            _np_ptr(o_src), _np_ptr(o_peer), _np_ptr(o_dst), _np_ptr(stage_ptr)),
-               "gae_halo_push_lists_host")
+    halo_pos = hp.n_local + np.arange(hp.n_halo, dtype=np.int64)
+    sst, p_src, p_peer, p_dst, stage_ptr = _send_lists(hp, halo_stage, halo_pos, n_stages, group)
     # row-block sub-CSRs (views of the local CSR; only rowptr is rebased)
     sub_rowptr, sub_col, sub_plan = [], [], []
     for s in range(n_stages):
@@ -211,16 +230,59 @@ def build_stage_plan(hp: HaloPlan, n_stages: int, group=None, seg_len: int = ops
         e0, e1 = int(rp[r0]), int(rp[r1])
         srp = (hp.rowptr[r0:r1 + 1] - e0).contiguous()
         scl = hp.col[e0:e1]
-        plan = None
-        if srp.is_cuda and r1 > r0:
-            plan = ops.build_hub_plan(srp, seg_len)
-            ops.order_segments_by_source(plan, srp, scl)
         sub_rowptr.append(srp)
         sub_col.append(scl)
-        sub_plan.append(plan)
-    return StagePlan(n_stages, bounds, sub_rowptr, sub_col, sub_plan, torch.from_numpy(halo_stage.copy()),
-                     torch.from_numpy(sst.copy()), torch.from_numpy(o_src[:m]).to(dev), torch.from_numpy(o_peer[:m]).to(dev),
-                     torch.from_numpy(o_dst[:m]).to(dev), stage_ptr)
+        sub_plan.append(_piece_plan(srp, scl, seg_len) if r1 > r0 else None)
+    return StagePlan("blocks", n_stages, bounds, [(bounds[s], bounds[s + 1] - bounds[s]) for s in range(n_stages)],
+                     sub_rowptr, sub_col, sub_plan, [False] * n_stages, torch.from_numpy(halo_stage.copy()),
+                     torch.from_numpy(halo_pos), sst, p_src, p_peer, p_dst, stage_ptr)
+
+
+DEFAULT_HOT_THRESHOLDS = (8,)
+
+
+def build_class_plan(hp: HaloPlan, thresholds=DEFAULT_HOT_THRESHOLDS, group=None,
+                     seg_len: int = ops.DEFAULT_SEG_LEN) -> StagePlan:
+    """Popularity-class stages.  A halo row referenced by >= thresholds[0] of this rank's edges is class 0,
+    by >= thresholds[1] class 1, ..., the rest the last class (thresholds descending).  On skewed graphs a
+    small class 0 carries most of the edges (R-MAT, 8 ranks: the 21 % of the halo rows referenced >= 8 times
+    carry 86 % of a rank's edges), so it is delivered first and the bulk of the aggregation -- local and
+    class-0 sources, piece 0 -- runs while the long tail of rarely used rows is still in flight; the tail
+    classes are then added into Y (pieces s > 0, accumulate).  The halo part of the buffer is laid out class
+    by class (ascending global id inside a class) and every piece is its own CSR over all local rows."""
+    dev = hp.rowptr.device
+    n_local, n_halo = hp.n_local, hp.n_halo
+    thresholds = sorted((int(t) for t in thresholds), reverse=True)
+    K = len(thresholds) + 1
+    col = hp.col.to(torch.int64)
+    is_halo = col >= n_local
+    cnt = torch.bincount(col[is_halo] - n_local, minlength=n_halo)
+    cls = torch.full((n_halo,), K - 1, dtype=torch.int64, device=dev)
+    for t in thresholds:
+        cls -= (cnt >= t).to(torch.int64)
+    order = torch.argsort(cls, stable=True)                    # class-major, ascending id inside a class
+    newpos = torch.empty(n_halo, dtype=torch.int64, device=dev)
+    newpos[order] = torch.arange(n_halo, dtype=torch.int64, device=dev)
+    deg = hp.rowptr[1:] - hp.rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n_local, dtype=torch.int64, device=dev), deg)
+    h = (col - n_local).clamp_(min=0)
+    ecls = torch.where(is_halo, cls[h] if n_halo else torch.zeros_like(col), torch.zeros_like(col))
+    newcol = torch.where(is_halo, n_local + (newpos[h] if n_halo else torch.zeros_like(col)), col)
+    del col, h, deg
+    sub_rowptr, sub_col, sub_plan = [], [], []
+    for k in range(K):
+        m = ecls == k
+        srp, scl = coo_to_csr_torch(newcol[m], rows[m], n_local, n_cols=n_local + n_halo)
+        sub_rowptr.append(srp)
+        sub_col.append(scl)
+        sub_plan.append(_piece_plan(srp, scl, seg_len))
+    del rows, newcol, ecls, is_halo
+    halo_stage = cls.to(torch.int32).cpu().numpy()
+    halo_pos = (n_local + newpos).cpu().numpy()
+    sst, p_src, p_peer, p_dst, stage_ptr = _send_lists(hp, halo_stage, halo_pos, K, group)
+    return StagePlan("classes", K, [0, n_local], [(0, n_local)] * K, sub_rowptr, sub_col, sub_plan,
+                     [k > 0 for k in range(K)], torch.from_numpy(halo_stage.copy()), torch.from_numpy(halo_pos.copy()),
+                     sst, p_src, p_peer, p_dst, stage_ptr)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,12 +359,18 @@ class HaloSpMM:
     exchange = "halo"
 
     def __init__(self, hp: HaloPlan, d: int, n_stages: int = DEFAULT_STAGES, group=None, push_ctas: int = 0,
-                 push_threads: int = 0, timeout_ms: int = 0, two_streams: bool = True):
+                 push_threads: int = 0, timeout_ms: int = 0, two_streams: bool = True, kind: str = "classes",
+                 thresholds=DEFAULT_HOT_THRESHOLDS):
         if d % 4 != 0:
             raise GaeError("the halo exchange needs 16-byte rows (d a multiple of 4)")
         self.hp, self.d, self.group = hp, d, group
         dev = hp.rowptr.device
-        self.sp = sp = build_stage_plan(hp, n_stages, group)
+        if kind == "classes":
+            self.sp = sp = build_class_plan(hp, thresholds, group)
+        elif kind == "blocks":
+            self.sp = sp = build_stage_plan(hp, n_stages, group)
+        else:
+            raise GaeError(f"unknown stage kind '{kind}'")
         self.X_ext = ops.alloc_rows(hp.n_local + hp.n_halo, d, dev)
         self.Y = ops.alloc_rows(hp.n_local, d, dev)
         # one segment workspace, a private slice per row block (consecutive blocks overlap in time)
@@ -338,7 +406,8 @@ class HaloSpMM:
         self._ex = ex
         blocks = (HaloBlockStruct * sp.n_stages)()
         for s in range(sp.n_stages):
-            blocks[s].row0, blocks[s].n_rows = sp.row_bounds[s], sp.row_bounds[s + 1] - sp.row_bounds[s]
+            blocks[s].row0, blocks[s].n_rows = sp.piece_rows[s]
+            blocks[s].accumulate = int(sp.accumulate[s])
             blocks[s].rowptr, blocks[s].col = sp.sub_rowptr[s].data_ptr(), sp.sub_col[s].data_ptr()
             p = sp.sub_plan[s]
             if p is not None and (p.n_seg > 0 or p.bins is not None):
@@ -355,7 +424,10 @@ class HaloSpMM:
 
     @property
     def X_halo(self) -> torch.Tensor:
-        return self.X_ext[self.hp.n_local:]
+        """Halo rows in the order of HaloPlan.halo_ids (a gathered copy when the buffer is laid out by class)."""
+        if self.sp.kind == "blocks":
+            return self.X_ext[self.hp.n_local:]
+        return self.X_ext[self.sp.halo_pos.to(self.X_ext.device)]
 
     def __call__(self) -> torch.Tensor:
         self.epoch += 1
@@ -588,7 +660,8 @@ class RmatPartition:
 
 def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device, exchange: str = "auto",
                          group=None, stages: int = DEFAULT_STAGES, push_ctas: int = 0,
-                         two_streams: bool = True) -> RmatPartition:
+                         two_streams: bool = True, kind: str = "classes",
+                         thresholds=DEFAULT_HOT_THRESHOLDS) -> RmatPartition:
     """Distributed R-MAT workload: every rank draws 1/P of the edge stream, edges are routed to the owner
     of their row, and the forward (rows = dst) and backward (rows = src) partitioned operators are built.
     exchange: "halo" (staged one-sided push with device flags, overlapped with `stages` row blocks),
@@ -617,8 +690,8 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
 
     def make_ops(mode):
         if mode == "halo":
-            return (HaloSpMM(hp_f, d, stages, group, push_ctas=push_ctas, two_streams=two_streams),
-                    HaloSpMM(hp_b, d, stages, group, push_ctas=push_ctas, two_streams=two_streams))
+            kw = dict(push_ctas=push_ctas, two_streams=two_streams, kind=kind, thresholds=thresholds)
+            return HaloSpMM(hp_f, d, stages, group, **kw), HaloSpMM(hp_b, d, stages, group, **kw)
         return PartitionedSpMM(hp_f, d, mode, group), PartitionedSpMM(hp_b, d, mode, group)
 
     if requested == "auto":
@@ -646,7 +719,10 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     desc = {"nccl": "pack + NCCL all-to-all-v of deduplicated halo rows, per SpMM",
             "push": "one-sided push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores) between two NCCL barriers, per SpMM",
             "p2p": "one-sided pull of deduplicated halo rows from peer HBM (CUDA IPC over NVLink), per SpMM",
-            "halo": f"one-sided staged push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores, "
-                    f"device-side release/acquire flags, no collective), {fwd_op.sp.n_stages if exchange == 'halo' else 0} "
-                    "stages overlapped with the row-block SpMMs, per SpMM"}[exchange]
+            "halo": "one-sided staged push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores, "
+                    "device-side release/acquire flags, no collective), per SpMM; "
+                    + (f"{fwd_op.sp.n_stages} {fwd_op.sp.kind}" if exchange == "halo" else "")
+                    + (f" (halo rows referenced >= {list(thresholds)} times first; the aggregation over local + hot sources "
+                       "overlaps the transfer of the rarely used rows, which are then added)" if exchange == "halo" and
+                       kind == "classes" else " overlapped with the row-block SpMMs" if exchange == "halo" else "")}[exchange]
     return RmatPartition(fwd_op, bwd_op, hp_f.n_edges, hp_f.n_local, hp_f.n_halo, desc, total_edges, d)

@@ -13,8 +13,9 @@
  *     legacy default stream).  The device is the caller's current device.
  *   - Return value: 0 = ok; negative = invalid argument (GAE_ERR_*); positive = cudaError_t.
  *     gae_last_error_string() gives a per-thread human-readable message.  No C++ exception
- *     crosses this boundary.  The library keeps no global mutable state besides tuning
- *     knobs (gae_set_tuning) and the per-thread error string; it is re-entrant.
+ *     crosses this boundary.  The library keeps no global mutable state besides the launch
+ *     counter: tuning knobs (gae_set_tuning) and the error string are per host thread; it is
+ *     re-entrant.
  *   - Matrices are row-major fp32 with an explicit leading dimension (elements).  The
  *     128-bit vector paths are taken when base pointers are 16-byte aligned and leading
  *     dimensions are multiples of 4; otherwise a scalar path computes the same result.
@@ -46,9 +47,10 @@ const char *gae_last_error_string(void);
 /* Tuning knobs used by bench sweeps.  Keys (default): "spmm_variant" (0: register gather; 1 / 2:
  * streaming cp.async.bulk / LDGSTS), "spmm_unroll" (4), "spmm_block" (64), "spmm_cache" (0),
  * "spmm_rows_per_warp" (1), "spmm_stages" (2), "spmm_bins" (1), "spmm_seg_order" (1), "spmm_fused"
- * (0; experimental single-launch form of the binned forward, not measured yet),
+ * (-1 = automatic; 1 / 0: single-launch form of the binned forward on / off),
  * "dec_splits" (0 = auto), "dec_rows" (2), "dec_mma" (1: decoder dense pass on the tensor cores for
- * d <= 16; 0: SIMT).  Results are independent of every knob up to fp32 summation order.
+ * d <= 16; 0: SIMT), "push_unroll" (4), "push_stream_ld" (1).  The knobs are PER HOST THREAD.
+ * Results are independent of every knob up to fp32 summation order.
  * Unknown keys return GAE_ERR_INVALID_ARG.  gae_get_tuning returns the value or -1. */
 int gae_set_tuning(const char *key, int32_t value);
 int32_t gae_get_tuning(const char *key);
@@ -262,8 +264,10 @@ int gae_ipc_close_handle(void *dev_ptr);
 /* ---- K7b: staged halo exchange fused with the row-block SpMMs (8e; the default multi-GPU path) ---- */
 /* Device-side protocol, no collective and no host sync on the data path.  Every rank maps its peers'
  * [local | halo] feature buffers and one FLAG block (GAE_HALO_FLAG_WORDS uint64, zero-initialised once)
- * per partitioned operator through CUDA IPC (gae_ipc_*).  Halo rows are tagged with the first row block
- * ("stage") of the consumer that reads them.  Per SpMM and rank:
+ * per partitioned operator through CUDA IPC (gae_ipc_*).  Halo rows are tagged with a "stage" by their
+ * consumer: either the first ROW BLOCK that reads them, or a POPULARITY CLASS (stage 0 = the few remote
+ * sources most of the edges point at; the consumer then sums class by class, blocks[s].accumulate = 1
+ * for s > 0).  Per SpMM and rank:
  *   gae_halo_push_f32     one persistent kernel: waits until every peer has consumed epoch-1, then pushes
  *                         the rows of stage 0, 1, ... into the peers' halo regions (posted NVLink stores)
  *                         and publishes landed[rank][stage] = epoch to every peer after each stage;
@@ -304,6 +308,8 @@ typedef struct gae_halo_block_t {
     const int32_t *col;           /* DEVICE: the block's slice of the [local | halo] column array       */
     const gae_hub_plan_t *plan;   /* hub plan of the block (may be NULL)                                */
     float *partial_ws;            /* its segment workspace                                              */
+    int32_t accumulate;           /* 0: Y[rows] = A_s X ; 1: Y[rows] += A_s X (a later PASS over the same rows:  */
+                                  /* the stages are then column classes of the halo instead of row blocks)      */
 } gae_halo_block_t;
 int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
 int gae_halo_wait_f32(const gae_halo_exchange_t *ex, int32_t stage, uint64_t epoch, void *stream);
@@ -328,9 +334,10 @@ int gae_halo_stage_tags_host(const int64_t *rowptr, const int32_t *col_local, in
                              int32_t *halo_stage);
 /* Send lists of the push kernel.  send_idx: my local rows requested by the peers, grouped by peer in
  * request order (send_counts[world]); send_stage: the stage of each entry at its consumer (NULL = 0);
- * dst_base[q]: row in q's buffer where my first row lands.  Output: entries sorted by stage and, within
- * a stage, interleaved over the peers; stage_ptr[n_stages+1]. */
-int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *send_stage,
+ * destination of entry j of peer q: send_dst[j] when given (the consumer chose its halo layout), else
+ * dst_base[q] + (position in q's request list).  Output: entries sorted by stage and, within a stage,
+ * interleaved over the peers; stage_ptr[n_stages+1]. */
+int gae_halo_push_lists_host(const int64_t *send_idx, const int32_t *send_stage, const int64_t *send_dst,
                              const int64_t *send_counts, const int64_t *dst_base, int32_t world,
                              int32_t n_stages, int64_t *out_src, int32_t *out_peer, int64_t *out_dst,
                              int64_t *stage_ptr);

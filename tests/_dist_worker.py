@@ -60,21 +60,32 @@ def run(rank, world, port, scale, n_edges, d, result_dir):
             # rows + destination indices through all-to-all-v), stage by stage, followed by the row-block
             # SpMM of that stage.  Same result as the unstaged op, and block b reads only halo rows that
             # stages <= b have delivered (the halo is poisoned beforehand).
-            for n_stages in (1, 2, 4, 7):
-                sp = parallel.build_stage_plan(plan, n_stages)
-                assert sp.row_bounds[0] == 0 and sp.row_bounds[-1] == plan.n_local
+            plans = [parallel.build_stage_plan(plan, k) for k in (1, 2, 4, 7)]
+            plans += [parallel.build_class_plan(plan, t) for t in ((8,), (16, 2), (10 ** 9,))]
+            for sp in plans:
+                n_stages = sp.n_stages
                 assert int(sp.stage_ptr[0]) == 0 and int(sp.stage_ptr[-1]) == int(plan.send_idx.numel())
                 assert sorted(sp.push_src.tolist()) == sorted(plan.send_idx.tolist())
                 assert sum(int(r[-1]) for r in sp.sub_rowptr) == plan.n_edges
-                op.X_halo.fill_(float("nan"))
-                op.Y.fill_(float("nan"))
+                assert sorted(sp.halo_pos.tolist()) == list(range(plan.n_local, plan.n_local + plan.n_halo))
+                if sp.kind == "blocks":
+                    assert sp.row_bounds[0] == 0 and sp.row_bounds[-1] == plan.n_local
+                else:
+                    # class-major halo layout; a piece reads local columns (piece 0 only) and its own class
+                    for k in range(sp.n_stages):
+                        c = sp.sub_col[k].to(torch.int64)
+                        hcols = c[c >= plan.n_local]
+                        assert k == 0 or hcols.numel() == c.numel()
+                        inv = torch.empty(plan.n_halo, dtype=torch.int64)
+                        inv[sp.halo_pos - plan.n_local] = torch.arange(plan.n_halo)
+                        assert bool((sp.halo_stage[inv[hcols - plan.n_local]] == k).all())
+                ext = torch.full((plan.n_local + plan.n_halo, d), float("nan"))
+                ext[:plan.n_local] = op.X_local
+                Ys = torch.full_like(op.Y, float("nan"))
                 landed = torch.zeros(plan.n_local + plan.n_halo, dtype=torch.int32)
                 for st in range(sp.n_stages):
                     e0, e1 = int(sp.stage_ptr[st]), int(sp.stage_ptr[st + 1])
                     peer = sp.push_peer[e0:e1].to(torch.int64)
-                    # interleaving: within a stage consecutive entries cycle over the peers that still have rows
-                    if e1 - e0 > world:
-                        assert len(set(peer[:min(world - 1, e1 - e0)].tolist())) == min(world - 1, len(set(peer.tolist())))
                     order = torch.argsort(peer, stable=True)
                     cnt = torch.bincount(peer, minlength=world)
                     rcnt = torch.empty_like(cnt)
@@ -87,25 +98,34 @@ def run(rank, world, port, scale, n_edges, d, result_dir):
                     parallel.all_to_all_v(got_dst, dsts, rcnt.tolist(), cnt.tolist())
                     assert got_dst.numel() == 0 or (int(got_dst.min()) >= plan.n_local and
                                                     int(got_dst.max()) < plan.n_local + plan.n_halo)
-                    op.X_ext[got_dst] = got_rows
+                    ext[got_dst] = got_rows
                     landed[got_dst] += 1
-                    assert torch.equal(sp.halo_stage[got_dst - plan.n_local].to(torch.int64),
-                                       torch.full_like(got_dst, st))
-                    r0, r1 = sp.row_bounds[st], sp.row_bounds[st + 1]
-                    if r1 > r0:
-                        _cpu_spmm(sp.sub_rowptr[st], sp.sub_col[st], op.X_ext, None, op.Y[r0:r1], None)
-                    assert not torch.isnan(op.Y[:r1]).any(), (name, n_stages, st)
+                    r0, nr = sp.piece_rows[st]
+                    if nr > 0:
+                        part_y = torch.empty((nr, d))
+                        _cpu_spmm(sp.sub_rowptr[st], sp.sub_col[st], ext, None, part_y, None)
+                        assert not torch.isnan(part_y).any(), (name, sp.kind, n_stages, st)   # only delivered rows were read
+                        if sp.accumulate[st]:
+                            Ys[r0:r0 + nr] += part_y
+                        else:
+                            Ys[r0:r0 + nr] = part_y
                 assert torch.equal(landed[plan.n_local:], torch.ones(plan.n_halo, dtype=torch.int32))   # every halo row once
-                assert torch.equal(op.Y, Y), (name, n_stages)
-                assert torch.equal(op.X_halo, Xg[plan.halo_ids])
-                # first-use tags: a halo row's stage is the block of the first local row that references it
-                deg = plan.rowptr[1:] - plan.rowptr[:-1]
-                erow = torch.repeat_interleave(torch.arange(plan.n_local), deg)
-                col64 = plan.col.to(torch.int64)
-                for h in range(0, plan.n_halo, max(1, plan.n_halo // 50)):
-                    first_row = int(erow[col64 == plan.n_local + h].min())
-                    blk = max(b for b in range(sp.n_stages) if sp.row_bounds[b] <= first_row)
-                    assert int(sp.halo_stage[h]) == blk
+                tol = 0.0 if sp.kind == "blocks" else 1e-5 * max(float(Y.abs().max()), 1.0)   # classes re-associate the sum
+                assert float((Ys - Y).abs().max()) <= tol, (name, sp.kind, n_stages)
+                assert torch.equal(ext[sp.halo_pos], Xg[plan.halo_ids])
+                if sp.kind == "blocks":
+                    # first-use tags: a halo row's stage is the block of the first local row that references it
+                    deg = plan.rowptr[1:] - plan.rowptr[:-1]
+                    erow = torch.repeat_interleave(torch.arange(plan.n_local), deg)
+                    col64 = plan.col.to(torch.int64)
+                    for h in range(0, plan.n_halo, max(1, plan.n_halo // 50)):
+                        first_row = int(erow[col64 == plan.n_local + h].min())
+                        blk = max(b for b in range(sp.n_stages) if sp.row_bounds[b] <= first_row)
+                        assert int(sp.halo_stage[h]) == blk
+                else:
+                    cnt_ref = torch.bincount(plan.col.to(torch.int64)[plan.col >= plan.n_local] - plan.n_local,
+                                             minlength=plan.n_halo)
+                    assert bool((sp.halo_stage[cnt_ref >= 10 ** 9] == 0).all())
         # global ground truth from the full edge stream
         S, D = synthetic.rmat_edges(scale, n_edges, seed=1)
         rp, col = O.coo_to_csr(S, D, n)

@@ -412,15 +412,20 @@ def test_halo_stage_tags_and_push_lists_host(lib_built):
     base = np.asarray([100, 0, 200], dtype=np.int64)
     o_src, o_peer, o_dst = np.zeros(5, dtype=np.int64), np.zeros(5, dtype=np.int32), np.zeros(5, dtype=np.int64)
     sptr = np.zeros(3, dtype=np.int64)
-    _lib.check(lib.gae_halo_push_lists_host(P(send_idx), P(stage), P(counts), P(base), 3, 2, P(o_src), P(o_peer), P(o_dst),
-                                            P(sptr)), "push lists")
+    _lib.check(lib.gae_halo_push_lists_host(P(send_idx), P(stage), None, P(counts), P(base), 3, 2, P(o_src), P(o_peer),
+                                            P(o_dst), P(sptr)), "push lists")
     assert sptr.tolist() == [0, 4, 5]
     # stage 0 interleaves the peers (k-th entry of each), stage 1 follows; dst = base[peer] + position in the request list
     assert o_src.tolist() == [7, 3, 9, 4, 8]
     assert o_peer.tolist() == [0, 2, 0, 2, 0]
     assert o_dst.tolist() == [100, 200, 102, 201, 101]
-    assert lib.gae_halo_push_lists_host(P(send_idx), P(np.asarray([0, 2, 0, 0, 0], dtype=np.int32)), P(counts), P(base), 3,
-                                        2, P(o_src), P(o_peer), P(o_dst), P(sptr)) == -1
+    # explicit destinations (the consumer chose its own halo layout)
+    dstpos = np.asarray([50, 51, 52, 60, 61], dtype=np.int64)
+    _lib.check(lib.gae_halo_push_lists_host(P(send_idx), P(stage), P(dstpos), P(counts), None, 3, 2, P(o_src), P(o_peer),
+                                            P(o_dst), P(sptr)), "push lists")
+    assert o_src.tolist() == [7, 3, 9, 4, 8] and o_dst.tolist() == [50, 60, 52, 61, 51]
+    assert lib.gae_halo_push_lists_host(P(send_idx), P(np.asarray([0, 2, 0, 0, 0], dtype=np.int32)), None, P(counts),
+                                        P(base), 3, 2, P(o_src), P(o_peer), P(o_dst), P(sptr)) == -1
     # descriptor validation happens before any launch (no GPU needed)
     ex = _lib.HaloExchangeStruct()
     assert lib.gae_halo_push_f32(ctypes.byref(ex), 1, None) == -1

@@ -22,8 +22,14 @@ def main():
     n = 1 << scale
     ok = True
     # (exchange, stages): "halo" = staged one-sided push with device flags, overlapped with `stages` row blocks
-    for exchange, stages in (("halo", 1), ("halo", 4), ("halo", 8), ("nccl", 1), ("push", 1), ("p2p", 1)):
-        part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange, stages=stages)
+    # stages > 0: row blocks; stages = 0 / -1: popularity classes with thresholds (8,) / (32, 4)
+    for exchange, stages in (("halo", 0), ("halo", -1), ("halo", 1), ("halo", 4), ("halo", 8), ("nccl", 1), ("push", 1),
+                             ("p2p", 1)):
+        kw = {}
+        if exchange == "halo":
+            kw = dict(kind="blocks") if stages > 0 else dict(kind="classes", thresholds=(8,) if stages == 0 else (32, 4))
+        part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange,
+                                             stages=max(stages, 1), **kw)
         Yf = part.fwd().clone()
         Yb = part.bwd().clone()
         if exchange == "halo":

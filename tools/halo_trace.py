@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--push-ctas", type=int, default=0)
     ap.add_argument("--one-stream", action="store_true")
     ap.add_argument("--push-threads", type=int, default=0)
+    ap.add_argument("--kind", type=str, default="classes")
+    ap.add_argument("--tune", type=str, default="")
+    ap.add_argument("--hot", type=str, default="8")
     ap.add_argument("--base-scale", type=int, default=22)
     ap.add_argument("--base-edges", type=int, default=100_000_000)
     args = ap.parse_args()
@@ -26,10 +29,14 @@ def main():
     dev = torch.device(f"cuda:{int(os.environ['LOCAL_RANK'])}")
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    from gae_dgl_b200 import ops, parallel
+    from gae_dgl_b200 import _lib as L, ops, parallel
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        L.set_tuning(k, int(v))
     scale = args.base_scale + int(round(math.log2(world)))
     part = parallel.build_rmat_partition(scale, args.base_edges * world, seed=1, d=64, device=dev, exchange="halo",
-                                         stages=args.stages, push_ctas=args.push_ctas, two_streams=not args.one_stream)
+                                         stages=args.stages, push_ctas=args.push_ctas, two_streams=not args.one_stream, kind=args.kind,
+                                         thresholds=tuple(int(x) for x in args.hot.split(",")))
     if args.push_threads:
         part.fwd_op._ex.push_threads = part.bwd_op._ex.push_threads = args.push_threads
     for _ in range(5):
@@ -37,7 +44,8 @@ def main():
         part.bwd()
     torch.cuda.synchronize()
     dist.barrier()
-    out = {"rank": rank, "stages": part.fwd_op.sp.n_stages, "fwd": part.fwd_op.trace(), "bwd": part.bwd_op.trace()}
+    out = {"rank": rank, "stages": part.fwd_op.sp.n_stages, "kind": part.fwd_op.sp.kind,
+           "piece_edges": [int(r[-1]) for r in part.fwd_op.sp.sub_rowptr], "fwd": part.fwd_op.trace(), "bwd": part.bwd_op.trace()}
     # the pieces on their own: the push alone (no consumer), and the row-block SpMMs alone (no waits)
     op = part.fwd_op
     st = torch.cuda.current_stream()
@@ -58,9 +66,10 @@ def main():
 
     def blocks_only():
         for s in range(sp.n_stages):
-            r0, r1 = sp.row_bounds[s], sp.row_bounds[s + 1]
-            if r1 > r0:
-                ops.spmm(sp.sub_rowptr[s], sp.sub_col[s], op.X_ext, sp.sub_plan[s], out=op.Y[r0:r1],
+            r0, nr = sp.piece_rows[s]
+            if nr > 0:
+                ops.spmm(sp.sub_rowptr[s], sp.sub_col[s], op.X_ext, sp.sub_plan[s], out=op.Y[r0:r0 + nr],
+                         accumulate=sp.accumulate[s],
                          partial_ws=op.ws if sp.sub_plan[s] is not None and sp.sub_plan[s].n_seg else None)
 
     out["blocks_only_ms"] = timed(blocks_only)
