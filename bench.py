@@ -57,9 +57,11 @@ def parse_args():
     p.add_argument("--stages", type=int, default=8,
                    help="N > 1, exchange 'halo': stages of the one-sided push overlapped with that many row-block SpMMs")
     p.add_argument("--push-ctas", type=int, default=0, help="N > 1, exchange 'halo': CTAs of the push kernel (0 = 64)")
-    p.add_argument("--halo-kind", type=str, default="classes", choices=["classes", "blocks"],
-                   help="exchange 'halo': stages = popularity classes of the halo rows (default) or row blocks")
-    p.add_argument("--hot", type=str, default="8", help="halo-kind classes: descending reference-count thresholds, e.g. 32,4")
+    p.add_argument("--halo-kind", type=str, default="fold", choices=["fold", "classes", "blocks"],
+                   help="exchange 'halo': hot rows copied + the tail folded by its owners (default), popularity classes "
+                        "of copied rows, or row blocks")
+    p.add_argument("--hot", type=str, default="", help="halo-kind fold: 'hot,fold' thresholds (default 16,2); classes: "
+                                                       "descending reference-count thresholds, e.g. 32,4 (default 8)")
     return p.parse_args()
 
 
@@ -489,15 +491,18 @@ def run_ours(args):
 
         exchange_desc = "none (single GPU)"
         halo_rows = 0
+        halo_stats = None
     else:
         from gae_dgl_b200 import parallel
         part = parallel.build_rmat_partition(scale, total_edges, seed=1, d=D_FEAT, device=dev,
                                              exchange=args.exchange, stages=args.stages, push_ctas=args.push_ctas,
-                                             kind=args.halo_kind, thresholds=tuple(int(x) for x in args.hot.split(",")))
+                                             kind=args.halo_kind,
+                                             thresholds=tuple(int(x) for x in args.hot.split(",")) if args.hot else None)
         fwd, bwd = part.fwd, part.bwd
         local_edges, local_rows = part.local_edges, part.local_rows
         exchange_desc = part.exchange_desc
         halo_rows = part.halo_rows
+        halo_stats = getattr(getattr(part.fwd_op, "sp", None), "stats", None)
 
     def step():
         fwd()
@@ -543,7 +548,7 @@ def run_ours(args):
     achieved = alg_bytes / (statistics.mean(fwd_ms) * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:      # an ncu capture of the single-GPU C4 launch; means nothing at N > 1
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -563,7 +568,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_of(scale, total_edges),
         "impl_detail": {"partition": "1d_vertex_blocks" if world > 1 else "single", "exchange": exchange_desc,
-                        "halo_rows_rank0": halo_rows, "local_rows_rank0": local_rows, "local_edges_rank0": local_edges,
+                        "halo_rows_rank0": halo_rows, "halo_exchange_rank0": halo_stats, "local_rows_rank0": local_rows, "local_edges_rank0": local_edges,
                         "tuning": {k: _lib.get_tuning(k) for k in ("spmm_unroll", "spmm_block", "spmm_cache",
                                                                    "spmm_rows_per_warp", "spmm_fused")}},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": sampler.summary(),

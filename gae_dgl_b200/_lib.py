@@ -60,6 +60,8 @@ class HaloExchangeStruct(Structure):
         ("send_src", c_void_p), ("send_peer", c_void_p), ("send_dst", c_void_p),
         ("stage_ptr", c_void_p), ("stage_done", c_void_p),
         ("push_ctas", c_int32), ("push_threads", c_int32), ("timeout_ms", c_int32),
+        ("pre_rowptr", c_void_p), ("pre_col", c_void_p), ("pre_plan", c_void_p), ("pre_ws", c_void_p),
+        ("pre_n_rows", c_int64), ("pre_row0", c_int64), ("pre_stage", c_int32),
     ]
 
 
@@ -126,6 +128,7 @@ SIGNATURES = {
     "gae_ipc_open_handle": (c_int, [POINTER(c_uint8 * 64), POINTER(c_void_p)]),
     "gae_ipc_close_handle": (c_int, [c_void_p]),
     "gae_halo_push_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
+    "gae_halo_push_range_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_int32, c_int32, c_void_p]),
     "gae_halo_wait_f32": (c_int, [POINTER(HaloExchangeStruct), c_int32, c_uint64, c_void_p]),
     "gae_halo_release_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
     "gae_halo_spmm_f32": (c_int, [POINTER(HaloExchangeStruct), POINTER(HaloBlockStruct), c_void_p, c_int64, c_uint64,

@@ -79,7 +79,7 @@ struct PushArgs {
     uint64_t *my_flags;
     uint32_t *stage_done;      // [n_stages] arrival counters, zero between launches
     int64_t ld_peer;
-    int32_t d4, world, rank, n_stages;
+    int32_t d4, world, rank, n_stages, first_stage;
     uint64_t epoch, timeout_ns;
     int64_t stage_ptr[GAE_HALO_MAX_STAGES + 1];
 };
@@ -98,12 +98,12 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const PushArgs a) {
         if ((int)threadIdx.x != a.rank) spin_until(a.my_flags + consumed_off(threadIdx.x), a.epoch - 1, a.timeout_ns, err);
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.my_flags[HALO_TRACE_OFF] = global_timer_ns();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.first_stage == 0) a.my_flags[HALO_TRACE_OFF] = global_timer_ns();
     constexpr int RPI = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int s = 0; s < a.n_stages; ++s) {
+    for (int s = a.first_stage; s < a.n_stages; ++s) {
         const int64_t e0 = a.stage_ptr[s], e1 = a.stage_ptr[s + 1];
         // the indices of the NEXT batch are loaded before the rows of the current one are moved
         int64_t base = e0 + warp * 32;
@@ -193,6 +193,11 @@ static int check_exchange(const gae_halo_exchange_t *ex) {
     for (int s = 0; s < ex->n_stages; ++s) GAE_CHECK_ARG(ex->stage_ptr[s + 1] >= ex->stage_ptr[s], "stage_ptr must be non-decreasing");
     const int64_t m = ex->stage_ptr[ex->n_stages];
     GAE_CHECK_ARG(m == 0 || (ex->send_src && ex->send_peer && ex->send_dst), "null send lists");
+    GAE_CHECK_ARG(ex->pre_n_rows >= 0, "pre_n_rows must be >= 0");
+    if (ex->pre_n_rows > 0) {
+        GAE_CHECK_ARG(ex->pre_rowptr && ex->pre_col && ex->pre_row0 > 0, "folding needs its CSR and staging rows");
+        GAE_CHECK_ARG(ex->pre_stage >= 0 && ex->pre_stage < ex->n_stages, "pre_stage out of range");
+    }
     return GAE_OK;
 }
 
@@ -207,14 +212,24 @@ using namespace gae;
 extern "C" int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream) {
     int rc = check_exchange(ex);
     if (rc) return rc;
+    return gae_halo_push_range_f32(ex, epoch, 0, ex->n_stages, stream);
+}
+
+extern "C" int gae_halo_push_range_f32(const gae_halo_exchange_t *ex, uint64_t epoch, int32_t stage0, int32_t stage1,
+                                       void *stream) {
+    int rc = check_exchange(ex);
+    if (rc) return rc;
     GAE_CHECK_ARG(epoch >= 1, "epochs count from 1");
-    if (ex->world == 1) return GAE_OK;
+    GAE_CHECK_ARG(stage0 >= 0 && stage0 <= stage1 && stage1 <= ex->n_stages, "bad stage range");
+    if (ex->world == 1 || stage0 == stage1) return GAE_OK;
     PushArgs a{};
     a.X = ex->x_local; a.ldx = ex->ld; a.send_src = ex->send_src; a.send_peer = ex->send_peer; a.send_dst = ex->send_dst;
     a.peer_x = ex->peer_x; a.peer_flags = ex->peer_flags; a.my_flags = ex->flags; a.stage_done = ex->stage_done;
-    a.ld_peer = ex->ld; a.d4 = ex->d / 4; a.world = ex->world; a.rank = ex->rank; a.n_stages = ex->n_stages;
+    a.ld_peer = ex->ld; a.d4 = ex->d / 4; a.world = ex->world; a.rank = ex->rank; a.n_stages = stage1;
+    a.first_stage = stage0;
     a.epoch = epoch; a.timeout_ns = timeout_of(ex);
     for (int s = 0; s <= ex->n_stages; ++s) a.stage_ptr[s] = ex->stage_ptr[s];
+    // a range with no entries still publishes its stages
     int ctas = ex->push_ctas > 0 ? ex->push_ctas : 64;
     int threads = ex->push_threads > 0 ? ex->push_threads : 256;
     if (threads > 512) threads = 512;
@@ -276,15 +291,31 @@ extern "C" int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_b
     GAE_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     GAE_CUDA(cudaEventCreateWithFlags(&pushed, cudaEventDisableTiming));
     GAE_CUDA(cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming));
-    // the push may start once everything queued on the compute stream (the producer of the local
-    // rows) is done; it then runs ahead of the row blocks
+    // The push may start once everything queued on the compute stream (the producer of the local
+    // rows) is done; it then runs ahead of the row blocks.  With folding, the stages before pre_stage
+    // go out at once, the folded rows are summed meanwhile (aux stream; compute stream if there is
+    // none) and the remaining stages follow.
+    const bool fold = ex->pre_n_rows > 0 && ex->world > 1;
+    const int split = fold ? ex->pre_stage : ex->n_stages;
+    cudaEvent_t folded = nullptr;
+    if (fold) GAE_CUDA(cudaEventCreateWithFlags(&folded, cudaEventDisableTiming));
+    const bool have_aux = aux_stream != nullptr && as != cs && as != ms;
     rc = (int)cudaEventRecord(ready, cs);
+    if (rc == GAE_OK && (two || (fold && have_aux))) rc = (int)cudaStreamWaitEvent(as, ready, 0);
     if (rc == GAE_OK && ex->world > 1) {
         rc = (int)cudaStreamWaitEvent(ms, ready, 0);
-        if (rc == GAE_OK) rc = gae_halo_push_f32(ex, epoch, comm_stream);
+        if (rc == GAE_OK) rc = gae_halo_push_range_f32(ex, epoch, 0, split, comm_stream);
+        if (rc == GAE_OK && fold) {
+            void *fs = have_aux ? aux_stream : compute_stream;
+            float *stage_rows = const_cast<float *>(ex->x_local) + ex->pre_row0 * ex->ld;
+            rc = gae_spmm_csr_f32(ex->pre_rowptr, ex->pre_col, nullptr, ex->x_local, ex->ld, stage_rows, ex->ld,
+                                  ex->pre_n_rows, ex->d, ex->pre_plan, ex->pre_ws, 0, fs);
+            if (rc == GAE_OK) rc = (int)cudaEventRecord(folded, (cudaStream_t)fs);
+            if (rc == GAE_OK) rc = (int)cudaStreamWaitEvent(ms, folded, 0);
+            if (rc == GAE_OK) rc = gae_halo_push_range_f32(ex, epoch, split, ex->n_stages, comm_stream);
+        }
         if (rc == GAE_OK) rc = (int)cudaEventRecord(pushed, ms);
     }
-    if (rc == GAE_OK && two) rc = (int)cudaStreamWaitEvent(as, ready, 0);
     // Row blocks alternate between the compute stream and the auxiliary stream: block s+1 depends on
     // its own flags only (its rows of Y and its segment workspace are private), so its first CTAs
     // fill the SMs that the tail of block s leaves idle instead of waiting behind a kernel boundary.
@@ -306,6 +337,7 @@ extern "C" int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_b
     cudaEventDestroy(ready);
     cudaEventDestroy(pushed);
     cudaEventDestroy(aux_done);
+    if (folded) cudaEventDestroy(folded);
     if (rc > 0) set_error("gae_halo_spmm_f32: CUDA error %d (%s)", rc, cudaGetErrorString((cudaError_t)rc));
     return rc;
 }

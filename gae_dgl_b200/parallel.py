@@ -158,6 +158,15 @@ class StagePlan:
     push_peer: torch.Tensor               # int32 [S]
     push_dst: torch.Tensor                # int64 [S]: row in the destination's [local | halo] buffer
     stage_ptr: np.ndarray                 # int64 [n_stages + 1] (host)
+    # kind "fold" only: the halo part of the buffer holds n_ext rows (copied hot / cold sources, then the
+    # folded rows the owners sum for me); behind it n_pre staging rows for the sums I owe my peers
+    n_ext: int = -1                       # halo rows in the buffer (-1: HaloPlan.n_halo)
+    n_pre: int = 0
+    pre_stage: int = 0
+    pre_rowptr: Optional[torch.Tensor] = None   # int64 [n_pre + 1]
+    pre_col: Optional[torch.Tensor] = None      # int32: my local rows
+    pre_plan: Optional[ops.HubPlan] = None
+    stats: Optional[dict] = None
 
 
 def edge_balanced_bounds(rowptr: np.ndarray, n_blocks: int) -> List[int]:
@@ -285,6 +294,142 @@ def build_class_plan(hp: HaloPlan, thresholds=DEFAULT_HOT_THRESHOLDS, group=None
                      sst, p_src, p_peer, p_dst, stage_ptr)
 
 
+DEFAULT_FOLD = (16, 2)       # (hot, fold): see build_fold_plan
+
+
+def build_fold_plan(hp: HaloPlan, hot: int = DEFAULT_FOLD[0], fold: int = DEFAULT_FOLD[1], group=None,
+                    seg_len: int = ops.DEFAULT_SEG_LEN) -> StagePlan:
+    """Popularity classes + sender-side FOLDING of the long tail (kind "fold", the default).
+
+    A remote source referenced by >= `hot` of my edges is copied as before (stage 0: few rows, most of the
+    edges).  The other remote edges mostly run from rarely used sources into my HUB rows, so for every (owner q,
+    my row j) with >= `fold` such edges I do not fetch the sources: q sums them for me over its own rows and
+    sends ONE folded row, which my CSR references as a single column.  What is left (cold sources of sparse
+    rows) is copied.  A vertex cover of the remote bipartite graph, chosen by two thresholds; R-MAT at 8 ranks:
+    0.56 of the deduplicated halo volume (hot 16, fold 2), and the folded edges leave my aggregation for the
+    owner's.  Stage 0 = hot rows, stage 1 = cold rows + folded rows; piece 0 = local + hot sources, piece 1
+    (accumulate) = cold sources + folded rows.  The sums I owe my peers are one more SpMM over my local rows
+    (pre_rowptr / pre_col) into staging rows behind my halo region; the push kernel reads them from there."""
+    lib = _lib.load()
+    dev = hp.rowptr.device
+    world, n_local, n_halo = hp.world, hp.n_local, hp.n_halo
+    hot, fold = max(int(hot), 1), max(int(fold), 2)
+    i64 = dict(dtype=torch.int64, device=dev)
+    nh = max(n_halo, 1)
+    col = hp.col.to(torch.int64)
+    is_halo = col >= n_local
+    h = (col - n_local).clamp_(min=0)
+    cnt = torch.bincount(h[is_halo], minlength=nh)
+    hot_row = cnt >= hot
+    if n_halo == 0:
+        hot_row[:] = False
+    owner = torch.zeros(nh, **i64)
+    owner[:n_halo] = torch.repeat_interleave(torch.arange(world, **i64), torch.tensor(hp.recv_counts, **i64))
+    b = torch.tensor(hp.bounds, **i64)
+    deg = hp.rowptr[1:] - hp.rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n_local, **i64), deg)
+    del deg, cnt
+    e_hot = is_halo & hot_row[h]
+    res = is_halo & ~e_hot
+    res_rows, res_h = rows[res], h[res]
+    del res
+    key = owner[res_h] * n_local + res_rows
+    uk, inv, kc = torch.unique(key, return_inverse=True, return_counts=True)
+    del key
+    folded_key = kc >= fold
+    e_fold = folded_key[inv] if inv.numel() else torch.zeros(0, dtype=torch.bool, device=dev)
+    cold_row = torch.zeros(nh, dtype=torch.bool, device=dev)
+    cold_row[res_h[~e_fold]] = True
+    n_hot, n_cold, n_fold = int(hot_row.sum()), int(cold_row.sum()), int(folded_key.sum())
+    n_ext = n_hot + n_cold + n_fold
+    pos = torch.full((nh,), -1, **i64)
+    pos[hot_row] = torch.arange(n_hot, **i64)
+    pos[cold_row] = n_hot + torch.arange(n_cold, **i64)
+    # my two pieces
+    m0 = ~is_halo | e_hot
+    c0 = torch.where(is_halo, n_local + pos[h], col)[m0]
+    rp0, cl0 = coo_to_csr_torch(c0, rows[m0], n_local, n_cols=n_local + n_ext)
+    del m0, c0, rows, col, is_halo, e_hot, h
+    fk = uk[folded_key]
+    f_cols = n_local + n_hot + n_cold + torch.arange(n_fold, **i64)
+    r1 = torch.cat([res_rows[~e_fold], fk % n_local])
+    c1 = torch.cat([n_local + pos[res_h[~e_fold]], f_cols])
+    rp1, cl1 = coo_to_csr_torch(c1, r1, n_local, n_cols=n_local + n_ext)
+    n_cold_edges = int((~e_fold).sum())
+    del r1, c1
+    # requests: (a) rows to copy, in halo order = grouped by owner; (b) rows to fold, ascending key = grouped by owner
+    sel = (hot_row | cold_row)[:n_halo]
+    sel_ids = torch.nonzero(sel).flatten()
+    copy_owner = owner[sel_ids]
+    copy_idx = hp.halo_ids[sel_ids] - b[copy_owner]
+    copy_stage = (~hot_row[sel_ids]).to(torch.int32)
+    copy_dst = n_local + pos[sel_ids]
+    fold_owner = torch.div(fk, max(n_local, 1), rounding_mode="floor")
+    fold_len = kc[folded_key]
+    slot_of_key = torch.cumsum(folded_key.to(torch.int64), 0) - 1
+    e_slot = slot_of_key[inv[e_fold]] if inv.numel() else torch.zeros(0, **i64)
+    e_order = torch.argsort(e_slot, stable=True)
+    e_h = res_h[e_fold][e_order]
+    fold_cols = (hp.halo_ids[e_h] - b[owner[e_h]]) if n_halo else torch.zeros(0, **i64)
+    n_fold_edges = int(e_h.numel())
+    del e_slot, e_order, e_h, inv, res_h, res_rows, e_fold
+    cnts = torch.stack([torch.bincount(copy_owner, minlength=world), torch.bincount(fold_owner, minlength=world),
+                        torch.zeros(world, **i64).index_add_(0, fold_owner, fold_len)], dim=1).contiguous()
+    got = torch.empty_like(cnts)
+    dist.all_to_all_single(got, cnts, group=group)
+    mine, theirs = cnts.cpu().tolist(), got.cpu().tolist()
+
+    def swap(t, k):
+        out = torch.empty(sum(x[k] for x in theirs), dtype=t.dtype, device=dev)
+        all_to_all_v(out, t.contiguous(), [x[k] for x in theirs], [x[k] for x in mine], group)
+        return out
+
+    g_idx, g_stage, g_dst = swap(copy_idx, 0), swap(copy_stage, 0), swap(copy_dst, 0)
+    g_flen, g_fdst, g_fcols = swap(fold_len, 1), swap(f_cols, 1), swap(fold_cols, 2)
+    # the sums I owe: one staging row per requested folded row, in peer order
+    n_pre = int(g_flen.numel())
+    pre_row0 = n_local + n_ext
+    pre_rowptr = torch.zeros(n_pre + 1, **i64)
+    pre_rowptr[1:] = torch.cumsum(g_flen, 0)
+    pre_col = g_fcols.to(torch.int32)
+    if n_pre and (int(g_fcols.min()) < 0 or int(g_fcols.max()) >= n_local):
+        raise GaeError("build_fold_plan: a peer asked me to sum rows I do not own")
+    # combined send lists per peer: [rows to copy | folded rows], then staged and interleaved
+    c_first = np.concatenate([[0], np.cumsum([x[0] for x in theirs])]).astype(np.int64)
+    f_first = np.concatenate([[0], np.cumsum([x[1] for x in theirs])]).astype(np.int64)
+    idx_np, st_np, dst_np = g_idx.cpu().numpy(), g_stage.cpu().numpy(), g_dst.cpu().numpy()
+    fdst_np = g_fdst.cpu().numpy()
+    s_idx, s_stage, s_dst, s_counts = [], [], [], []
+    for q in range(world):
+        c0_, c1_, f0_, f1_ = c_first[q], c_first[q + 1], f_first[q], f_first[q + 1]
+        s_idx += [idx_np[c0_:c1_], pre_row0 + np.arange(f0_, f1_, dtype=np.int64)]
+        s_stage += [st_np[c0_:c1_], np.ones(f1_ - f0_, dtype=np.int32)]
+        s_dst += [dst_np[c0_:c1_], fdst_np[f0_:f1_]]
+        s_counts.append(int(c1_ - c0_ + f1_ - f0_))
+    send_idx = np.ascontiguousarray(np.concatenate(s_idx), dtype=np.int64)
+    sst = np.ascontiguousarray(np.concatenate(s_stage), dtype=np.int32)
+    sdst = np.ascontiguousarray(np.concatenate(s_dst), dtype=np.int64)
+    sc = np.asarray(s_counts, dtype=np.int64)
+    m = int(send_idx.size)
+    o_src, o_peer, o_dst = (np.zeros(max(m, 1), dtype=np.int64), np.zeros(max(m, 1), dtype=np.int32),
+                            np.zeros(max(m, 1), dtype=np.int64))
+    stage_ptr = np.zeros(3, dtype=np.int64)
+    _lib.check(lib.gae_halo_push_lists_host(_np_ptr(send_idx), _np_ptr(sst), _np_ptr(sdst), _np_ptr(sc), None, world, 2,
+                                            _np_ptr(o_src), _np_ptr(o_peer), _np_ptr(o_dst), _np_ptr(stage_ptr)),
+               "gae_halo_push_lists_host")
+    halo_stage = torch.where(hot_row, 0, torch.where(cold_row, 1, -1))[:n_halo].to(torch.int32).cpu()
+    halo_pos = torch.where(pos >= 0, n_local + pos, -1)[:n_halo].cpu()
+    stats = {"halo_rows_dedup": n_halo, "hot_rows": n_hot, "cold_rows": n_cold, "folded_rows_in": n_fold,
+             "rows_in": n_ext, "rows_out": m, "folded_rows_out": n_pre, "folded_edges_out": int(pre_col.numel()),
+             "folded_edges_in": n_fold_edges, "cold_edges": n_cold_edges, "hot": hot, "fold": fold}
+    return StagePlan("fold", 2, [0, n_local], [(0, n_local)] * 2, [rp0, rp1], [cl0, cl1],
+                     [_piece_plan(rp0, cl0, seg_len), _piece_plan(rp1, cl1, seg_len)], [False, True], halo_stage, halo_pos,
+                     torch.from_numpy(sst.copy()), torch.from_numpy(o_src[:m]).to(dev), torch.from_numpy(o_peer[:m]).to(dev),
+                     torch.from_numpy(o_dst[:m]).to(dev), stage_ptr, n_ext=n_ext, n_pre=n_pre, pre_stage=1,
+                     pre_rowptr=pre_rowptr, pre_col=pre_col,
+                     pre_plan=_piece_plan(pre_rowptr, pre_col, seg_len) if n_pre else None, stats=stats)
+
+
 # ------------------------------------------------------------------------------------------------
 # peer memory (CUDA IPC) shared by the operators of one process
 # ------------------------------------------------------------------------------------------------
@@ -359,19 +504,23 @@ class HaloSpMM:
     exchange = "halo"
 
     def __init__(self, hp: HaloPlan, d: int, n_stages: int = DEFAULT_STAGES, group=None, push_ctas: int = 0,
-                 push_threads: int = 0, timeout_ms: int = 0, two_streams: bool = True, kind: str = "classes",
-                 thresholds=DEFAULT_HOT_THRESHOLDS):
+                 push_threads: int = 0, timeout_ms: int = 0, two_streams: bool = True, kind: str = "fold",
+                 thresholds=None):
         if d % 4 != 0:
             raise GaeError("the halo exchange needs 16-byte rows (d a multiple of 4)")
         self.hp, self.d, self.group = hp, d, group
         dev = hp.rowptr.device
-        if kind == "classes":
-            self.sp = sp = build_class_plan(hp, thresholds, group)
+        if kind == "fold":
+            hot, fold = tuple(thresholds) if thresholds else DEFAULT_FOLD
+            self.sp = sp = build_fold_plan(hp, hot, fold, group)
+        elif kind == "classes":
+            self.sp = sp = build_class_plan(hp, thresholds or DEFAULT_HOT_THRESHOLDS, group)
         elif kind == "blocks":
             self.sp = sp = build_stage_plan(hp, n_stages, group)
         else:
             raise GaeError(f"unknown stage kind '{kind}'")
-        self.X_ext = ops.alloc_rows(hp.n_local + hp.n_halo, d, dev)
+        self.n_ext = sp.n_ext if sp.n_ext >= 0 else hp.n_halo          # halo rows held in the buffer
+        self.X_ext = ops.alloc_rows(hp.n_local + self.n_ext + sp.n_pre, d, dev)
         self.Y = ops.alloc_rows(hp.n_local, d, dev)
         # one segment workspace, a private slice per row block (consecutive blocks overlap in time)
         seg_counts = [p.n_seg if p is not None else 0 for p in sp.sub_plan]
@@ -403,6 +552,14 @@ class HaloSpMM:
         self._stage_done = torch.zeros(sp.n_stages, dtype=torch.int32, device=dev)
         ex.stage_done = self._stage_done.data_ptr()
         ex.push_ctas, ex.push_threads, ex.timeout_ms = int(push_ctas), int(push_threads), int(timeout_ms)
+        if sp.n_pre > 0:
+            ex.pre_rowptr, ex.pre_col = sp.pre_rowptr.data_ptr(), sp.pre_col.data_ptr()
+            ex.pre_n_rows, ex.pre_row0, ex.pre_stage = sp.n_pre, hp.n_local + self.n_ext, sp.pre_stage
+            pp = sp.pre_plan
+            if pp is not None and (pp.n_seg > 0 or pp.bins is not None):
+                ex.pre_plan = ctypes.addressof(pp.struct)
+            self._pre_ws = pp.workspace(d, dev) if pp is not None and pp.n_seg > 0 else None
+            ex.pre_ws = self._pre_ws.data_ptr() if self._pre_ws is not None else None
         self._ex = ex
         blocks = (HaloBlockStruct * sp.n_stages)()
         for s in range(sp.n_stages):
@@ -427,6 +584,8 @@ class HaloSpMM:
         """Halo rows in the order of HaloPlan.halo_ids (a gathered copy when the buffer is laid out by class)."""
         if self.sp.kind == "blocks":
             return self.X_ext[self.hp.n_local:]
+        if self.sp.kind == "fold":
+            raise GaeError("kind 'fold' keeps only part of the halo rows (the rest arrives folded)")
         return self.X_ext[self.sp.halo_pos.to(self.X_ext.device)]
 
     def __call__(self) -> torch.Tensor:
@@ -658,10 +817,23 @@ class RmatPartition:
                 "api": "PartitionedSpMM with pinned host X/dY in, Y/dX out per rank; graph + halo plan resident"}
 
 
+def _halo_desc(op: "HaloSpMM") -> str:
+    sp = op.sp
+    if sp.kind == "fold":
+        st = sp.stats
+        return (f"stages: remote sources referenced >= {st['hot']} times are copied first, the rest of the remote edges "
+                f"arrive as rows FOLDED by their owner (one sum per (owner, destination row) with >= {st['fold']} such "
+                f"edges) or as cold copies; rank 0 receives {st['rows_in']} rows instead of {st['halo_rows_dedup']} "
+                "deduplicated halo rows; the aggregation over local + hot sources overlaps the transfer of the rest")
+    if sp.kind == "classes":
+        return (f"{sp.n_stages} popularity classes of deduplicated halo rows (hot rows first; the aggregation over local + "
+                "hot sources overlaps the transfer of the rarely used rows, which are then added)")
+    return f"{sp.n_stages} row-block stages of deduplicated halo rows overlapped with the row-block SpMMs"
+
+
 def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device, exchange: str = "auto",
                          group=None, stages: int = DEFAULT_STAGES, push_ctas: int = 0,
-                         two_streams: bool = True, kind: str = "classes",
-                         thresholds=DEFAULT_HOT_THRESHOLDS) -> RmatPartition:
+                         two_streams: bool = True, kind: str = "fold", thresholds=None) -> RmatPartition:
     """Distributed R-MAT workload: every rank draws 1/P of the edge stream, edges are routed to the owner
     of their row, and the forward (rows = dst) and backward (rows = src) partitioned operators are built.
     exchange: "halo" (staged one-sided push with device flags, overlapped with `stages` row blocks),
@@ -719,10 +891,6 @@ def build_rmat_partition(scale: int, total_edges: int, seed: int, d: int, device
     desc = {"nccl": "pack + NCCL all-to-all-v of deduplicated halo rows, per SpMM",
             "push": "one-sided push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores) between two NCCL barriers, per SpMM",
             "p2p": "one-sided pull of deduplicated halo rows from peer HBM (CUDA IPC over NVLink), per SpMM",
-            "halo": "one-sided staged push of deduplicated halo rows into peer HBM (CUDA IPC, posted NVLink stores, "
-                    "device-side release/acquire flags, no collective), per SpMM; "
-                    + (f"{fwd_op.sp.n_stages} {fwd_op.sp.kind}" if exchange == "halo" else "")
-                    + (f" (halo rows referenced >= {list(thresholds)} times first; the aggregation over local + hot sources "
-                       "overlaps the transfer of the rarely used rows, which are then added)" if exchange == "halo" and
-                       kind == "classes" else " overlapped with the row-block SpMMs" if exchange == "halo" else "")}[exchange]
+            "halo": "one-sided staged push into peer HBM (CUDA IPC, posted NVLink stores, device-side release/acquire "
+                    "flags, no collective), per SpMM; " + (_halo_desc(fwd_op) if exchange == "halo" else "")}[exchange]
     return RmatPartition(fwd_op, bwd_op, hp_f.n_edges, hp_f.n_local, hp_f.n_halo, desc, total_edges, d)

@@ -301,6 +301,21 @@ typedef struct gae_halo_exchange_t {
     int32_t push_ctas;            /* 0 = default (64)                                                   */
     int32_t push_threads;         /* 0 = default (256)                                                  */
     int32_t timeout_ms;           /* 0 = default (10000)                                                */
+    /* Optional sender-side FOLDING (pre_n_rows > 0).  A consumer may ask an owner not for source rows but
+     * for their SUM over the edges into one of its destination rows: on skewed graphs the rarely used remote
+     * sources mostly feed hub destinations, so one folded row replaces many copied ones (R-MAT, 8 ranks: the
+     * exchange shrinks to ~0.56 of the deduplicated halo).  The owner computes the folded rows with the
+     * ordinary SpMM -- CSR (pre_rowptr, pre_col) over its LOCAL rows -- into staging rows
+     * [pre_row0, pre_row0 + pre_n_rows) of its own buffer, behind the halo region; send entries of stages
+     * >= pre_stage may name staging rows as their source.  gae_halo_spmm_f32 runs that SpMM on aux_stream
+     * while stages < pre_stage are already being pushed. */
+    const int64_t *pre_rowptr;    /* DEVICE [pre_n_rows+1]                                              */
+    const int32_t *pre_col;       /* DEVICE: local source rows                                          */
+    const gae_hub_plan_t *pre_plan;
+    float *pre_ws;                /* segment workspace of pre_plan                                      */
+    int64_t pre_n_rows;           /* 0 = no folding                                                     */
+    int64_t pre_row0;
+    int32_t pre_stage;
 } gae_halo_exchange_t;
 typedef struct gae_halo_block_t {
     int64_t row0, n_rows;         /* local row range of the block                                       */
@@ -312,6 +327,9 @@ typedef struct gae_halo_block_t {
                                   /* the stages are then column classes of the halo instead of row blocks)      */
 } gae_halo_block_t;
 int gae_halo_push_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
+/* Stages [stage0, stage1) only (the folded rows of later stages may not exist yet). */
+int gae_halo_push_range_f32(const gae_halo_exchange_t *ex, uint64_t epoch, int32_t stage0, int32_t stage1,
+                            void *stream);
 int gae_halo_wait_f32(const gae_halo_exchange_t *ex, int32_t stage, uint64_t epoch, void *stream);
 int gae_halo_release_f32(const gae_halo_exchange_t *ex, uint64_t epoch, void *stream);
 int gae_halo_spmm_f32(const gae_halo_exchange_t *ex, const gae_halo_block_t *blocks /* HOST [n_stages] */,

@@ -126,6 +126,65 @@ def run(rank, world, port, scale, n_edges, d, result_dir):
                     cnt_ref = torch.bincount(plan.col.to(torch.int64)[plan.col >= plan.n_local] - plan.n_local,
                                              minlength=plan.n_halo)
                     assert bool((sp.halo_stage[cnt_ref >= 10 ** 9] == 0).all())
+            # folded exchange (kind "fold", the default of HaloSpMM): hot rows copied, the tail summed by its
+            # owners.  Emulated the same way: the sums I owe (pre CSR over my local rows) go into staging rows
+            # behind my halo region, then the two stages are pushed and the two pieces aggregated.
+            for hot, fold in ((4, 2), (16, 2), (2, 3), (1, 2), (10 ** 9, 2), (10 ** 9, 10 ** 9)):
+                sp = parallel.build_fold_plan(plan, hot, fold)
+                assert sp.kind == "fold" and sp.n_stages == 2 and sp.accumulate == [False, True] and sp.pre_stage == 1
+                n_ext, n_pre, base = sp.n_ext, sp.n_pre, plan.n_local + sp.n_ext
+                st_ = sp.stats
+                assert st_["rows_in"] == n_ext == st_["hot_rows"] + st_["cold_rows"] + st_["folded_rows_in"]
+                # every one of my edges is aggregated exactly once: by me (pieces) or by an owner (folded)
+                assert int(sp.sub_rowptr[0][-1]) + st_["cold_edges"] + st_["folded_edges_in"] == plan.n_edges
+                assert int(sp.sub_rowptr[1][-1]) == st_["cold_edges"] + st_["folded_rows_in"]
+                tot = torch.tensor([n_ext, int(sp.stage_ptr[-1]), st_["folded_edges_in"], st_["folded_edges_out"]])
+                dist.all_reduce(tot)
+                assert int(tot[0]) == int(tot[1]) and int(tot[2]) == int(tot[3])
+                assert (hot, fold) != (4, 2) or int(tot[2]) > 0          # the small test graph does fold something
+                if hot == 1:
+                    assert n_ext == plan.n_halo and n_pre == 0 and st_["cold_rows"] == 0
+                if fold >= 10 ** 9:
+                    assert n_ext == plan.n_halo and n_pre == 0 and st_["folded_rows_in"] == 0
+                ext = torch.full((base + n_pre, d), float("nan"))
+                ext[:plan.n_local] = op.X_local
+                if n_pre:
+                    assert int(sp.pre_col.max()) < plan.n_local and int(sp.pre_rowptr[-1]) == sp.pre_col.numel()
+                    pre = torch.empty((n_pre, d))
+                    _cpu_spmm(sp.pre_rowptr, sp.pre_col, ext[:plan.n_local], None, pre, None)
+                    ext[base:] = pre
+                Ys = torch.full_like(op.Y, float("nan"))
+                landed = torch.zeros(base, dtype=torch.int32)
+                for st in range(2):
+                    e0, e1 = int(sp.stage_ptr[st]), int(sp.stage_ptr[st + 1])
+                    srcs = sp.push_src[e0:e1]
+                    assert st >= sp.pre_stage or srcs.numel() == 0 or int(srcs.max()) < plan.n_local
+                    assert srcs.numel() == 0 or bool(((srcs < plan.n_local) | (srcs >= base)).all())
+                    peer = sp.push_peer[e0:e1].to(torch.int64)
+                    order = torch.argsort(peer, stable=True)
+                    cnt = torch.bincount(peer, minlength=world)
+                    rcnt = torch.empty_like(cnt)
+                    dist.all_to_all_single(rcnt, cnt)
+                    rows = ext.index_select(0, srcs[order])
+                    dsts = sp.push_dst[e0:e1][order].contiguous()
+                    got_rows = torch.empty((int(rcnt.sum()), d))
+                    got_dst = torch.empty(int(rcnt.sum()), dtype=torch.int64)
+                    parallel.all_to_all_v(got_rows, rows, rcnt.tolist(), cnt.tolist())
+                    parallel.all_to_all_v(got_dst, dsts, rcnt.tolist(), cnt.tolist())
+                    assert got_dst.numel() == 0 or (int(got_dst.min()) >= plan.n_local and int(got_dst.max()) < base)
+                    ext[got_dst] = got_rows
+                    landed[got_dst] += 1
+                    part_y = torch.empty((plan.n_local, d))
+                    _cpu_spmm(sp.sub_rowptr[st], sp.sub_col[st], ext[:base], None, part_y, None)
+                    assert not torch.isnan(part_y).any(), (name, "fold", hot, fold, st)
+                    Ys = part_y if st == 0 else Ys + part_y
+                assert torch.equal(landed[plan.n_local:], torch.ones(n_ext, dtype=torch.int32))
+                tol = 1e-5 * max(float(Y.abs().max()), 1.0)
+                assert float((Ys - Y).abs().max()) <= tol, (name, "fold", hot, fold)
+                # the copied rows are the owners' rows; rows that arrive folded have no slot
+                kept = sp.halo_pos >= 0
+                assert torch.equal(ext[sp.halo_pos[kept]], Xg[plan.halo_ids[kept]])
+                assert int(kept.sum()) == st_["hot_rows"] + st_["cold_rows"]
         # global ground truth from the full edge stream
         S, D = synthetic.rmat_edges(scale, n_edges, seed=1)
         rp, col = O.coo_to_csr(S, D, n)

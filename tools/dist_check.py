@@ -22,12 +22,15 @@ def main():
     n = 1 << scale
     ok = True
     # (exchange, stages): "halo" = staged one-sided push with device flags, overlapped with `stages` row blocks
-    # stages > 0: row blocks; stages = 0 / -1: popularity classes with thresholds (8,) / (32, 4)
-    for exchange, stages in (("halo", 0), ("halo", -1), ("halo", 1), ("halo", 4), ("halo", 8), ("nccl", 1), ("push", 1),
+    # stages > 0: row blocks; stages = 0 / -1: popularity classes with thresholds (8,) / (32, 4);
+    # stages = -2 / -3: hot rows copied + the tail folded by its owners, thresholds (16, 2) / (4, 3)
+    for exchange, stages in (("halo", -2), ("halo", -3), ("halo", 0), ("halo", -1), ("halo", 1), ("halo", 4), ("halo", 8), ("nccl", 1), ("push", 1),
                              ("p2p", 1)):
         kw = {}
         if exchange == "halo":
-            kw = dict(kind="blocks") if stages > 0 else dict(kind="classes", thresholds=(8,) if stages == 0 else (32, 4))
+            kw = (dict(kind="blocks") if stages > 0 else
+                  dict(kind="classes", thresholds=(8,) if stages == 0 else (32, 4)) if stages >= -1 else
+                  dict(kind="fold", thresholds=(16, 2) if stages == -2 else (4, 3)))
         part = parallel.build_rmat_partition(scale, n_edges, seed=1, d=d, device=dev, exchange=exchange,
                                              stages=max(stages, 1), **kw)
         Yf = part.fwd().clone()

@@ -19,9 +19,9 @@ def main():
     ap.add_argument("--push-ctas", type=int, default=0)
     ap.add_argument("--one-stream", action="store_true")
     ap.add_argument("--push-threads", type=int, default=0)
-    ap.add_argument("--kind", type=str, default="classes")
+    ap.add_argument("--kind", type=str, default="fold")
     ap.add_argument("--tune", type=str, default="")
-    ap.add_argument("--hot", type=str, default="8")
+    ap.add_argument("--hot", type=str, default="")
     ap.add_argument("--base-scale", type=int, default=22)
     ap.add_argument("--base-edges", type=int, default=100_000_000)
     args = ap.parse_args()
@@ -36,7 +36,7 @@ def main():
     scale = args.base_scale + int(round(math.log2(world)))
     part = parallel.build_rmat_partition(scale, args.base_edges * world, seed=1, d=64, device=dev, exchange="halo",
                                          stages=args.stages, push_ctas=args.push_ctas, two_streams=not args.one_stream, kind=args.kind,
-                                         thresholds=tuple(int(x) for x in args.hot.split(",")))
+                                         thresholds=tuple(int(x) for x in args.hot.split(",")) if args.hot else None)
     if args.push_threads:
         part.fwd_op._ex.push_threads = part.bwd_op._ex.push_threads = args.push_threads
     for _ in range(5):
@@ -73,8 +73,15 @@ def main():
                          partial_ws=op.ws if sp.sub_plan[s] is not None and sp.sub_plan[s].n_seg else None)
 
     out["blocks_only_ms"] = timed(blocks_only)
-    out["whole_plan_spmm_ms"] = timed(lambda: ops.spmm(op.hp.rowptr, op.hp.col, op.X_ext, op.hp.plan, out=op.Y,
-                                                       partial_ws=op.hp.plan.workspace(64, dev)))
+    xfull = ops.alloc_rows(op.hp.n_local + op.hp.n_halo, 64, dev).normal_()     # the unfolded [local | halo] buffer
+    wsf = op.hp.plan.workspace(64, dev)
+    out["whole_plan_spmm_ms"] = timed(lambda: ops.spmm(op.hp.rowptr, op.hp.col, xfull, op.hp.plan, out=op.Y, partial_ws=wsf))
+    del xfull
+    if sp.n_pre:
+        out["exchange"] = sp.stats
+        pre_out = op.X_ext[op.hp.n_local + op.n_ext:]
+        out["fold_spmm_only_ms"] = timed(lambda: ops.spmm(sp.pre_rowptr, sp.pre_col, op.X_ext, sp.pre_plan, out=pre_out,
+                                                          partial_ws=op._pre_ws))
     out["op_ms"] = timed(lambda: op())
     op.check()
     # the push alone: nothing else runs on the GPU; every stage is waited for, then the halo is released
@@ -84,7 +91,7 @@ def main():
 
     def push_only():
         op.epoch += 1
-        _lib.check(lib.gae_halo_push_f32(ctypes.byref(op._ex), op.epoch, op._comm.cuda_stream), "push")
+        _lib.check(lib.gae_halo_push_f32(ctypes.byref(op._ex), op.epoch, op._comm.cuda_stream), "push")   # staging rows as they are
         for s in range(sp.n_stages):
             _lib.check(lib.gae_halo_wait_f32(ctypes.byref(op._ex), s, op.epoch, st.cuda_stream), "wait")
         _lib.check(lib.gae_halo_release_f32(ctypes.byref(op._ex), op.epoch, st.cuda_stream), "release")
