@@ -48,6 +48,7 @@ class StepDesc(Structure):
         ("dropout_p", c_float),
         ("pos_weight", c_float),
         ("per_graph", c_int32),
+        ("x_aggregated", c_int32),
     ]
 
 

@@ -46,7 +46,7 @@ static int64_t carve(const gae_step_desc_t *d, int64_t n, const gae_hub_plan_t *
     for (int l = 0; l <= L; ++l) max_d = d->dims[l] > max_d ? d->dims[l] : max_d;
     StepBuffers sb{};
     for (int l = 0; l < L; ++l) {
-        sb.Y[l] = b.take<float>(n * ld4(d->dims[l]));
+        sb.Y[l] = (l == 0 && d->x_aggregated) ? nullptr : b.take<float>(n * ld4(d->dims[l]));
         sb.H[l] = (l == L - 1) ? nullptr : b.take<float>(n * ld4(d->dims[l + 1]));
         sb.dH[l] = b.take<float>(n * ld4(d->dims[l + 1]));
         sb.dY[l] = (l == 0) ? nullptr : b.take<float>(n * ld4(d->dims[l]));
@@ -107,11 +107,16 @@ extern "C" int gae_step_fwd_bwd_f32(const gae_step_desc_t *desc, int64_t n, cons
     int64_t ldh = ldx;
     for (int l = 0; l < L; ++l) {
         const int din = desc->dims[l], dout = desc->dims[l + 1];
-        rc = gae_spmm_csr_f32(rowptr, col, nullptr, h, ldh, sb.Y[l], ld4(din), n, din, plan, sb.hub_ws, 0, stream);
-        if (rc) return rc;
+        const bool pre = l == 0 && desc->x_aggregated;       // X is A X already
+        const float *y = pre ? X : sb.Y[l];
+        const int64_t ldy = pre ? ldx : ld4(din);
+        if (!pre) {
+            rc = gae_spmm_csr_f32(rowptr, col, nullptr, h, ldh, sb.Y[l], ld4(din), n, din, plan, sb.hub_ws, 0, stream);
+            if (rc) return rc;
+        }
         float *out = (l == L - 1) ? Z_out : sb.H[l];
         const int64_t ldo = (l == L - 1) ? ldz : ld4(dout);
-        rc = gae_linear_fwd_f32(sb.Y[l], ld4(din), W[l], b[l], out, ldo, n, din, dout, desc->acts[l], stream);
+        rc = gae_linear_fwd_f32(y, ldy, W[l], b[l], out, ldo, n, din, dout, desc->acts[l], stream);
         if (rc) return rc;
         h = out;
         ldh = ldo;
@@ -139,7 +144,8 @@ extern "C" int gae_step_fwd_bwd_f32(const gae_step_desc_t *desc, int64_t n, cons
         const int din = desc->dims[l], dout = desc->dims[l + 1];
         const float *Hout = (l == L - 1) ? Z_out : sb.H[l];
         const int64_t ldo = (l == L - 1) ? ldz : ld4(dout);
-        rc = gae_linear_bwd_f32(sb.Y[l], ld4(din), W[l], Hout, ldo, sb.dH[l], ld4(dout), sb.dY[l], ld4(din), dW[l], db[l],
+        const bool pre = l == 0 && desc->x_aggregated;
+        rc = gae_linear_bwd_f32(pre ? X : sb.Y[l], pre ? ldx : ld4(din), W[l], Hout, ldo, sb.dH[l], ld4(dout), sb.dY[l], ld4(din), dW[l], db[l],
                                 sb.lin_ws, sb.lin_ws_bytes, n, din, dout, desc->acts[l], stream);
         if (rc) return rc;
         if (l > 0) {   // dH_{l-1} = A^T dY_l ; the input features are a leaf (gae.py:50)

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import lazy, ops
 from .graph import DGLGraph, function as fn
 
 _IDENTITY = lambda x: x  # noqa: E731  (gae.py:43,45,47 use `lambda x:x`)
@@ -96,11 +96,22 @@ class InnerProductDecoder(nn.Module):
         generator (so torch.manual_seed controls it) and advanced on-stream by every draw: no
         per-step host RNG call, and captured CUDA graphs draw a fresh mask on each replay."""
         st = getattr(self, "_philox", None)
-        if st is None or st.device != device:
+        if st is None:
             seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
             st = torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
             self._philox = st
+        elif st.device != device:
+            st = self._philox = st.to(device)          # the stream continues where it was (no re-seeding)
         return st
+
+    def rng_state_dict(self) -> Optional[torch.Tensor]:
+        """{seed, offset} of the dropout stream (host copy) for checkpoints; None before the first draw."""
+        st = getattr(self, "_philox", None)
+        return None if st is None else st.detach().cpu().clone()
+
+    def load_rng_state(self, state: Optional[torch.Tensor], device=None) -> None:
+        if state is not None:
+            self._philox = state.to(device if device is not None else state.device).clone()
 
     def forward(self, z, mask: Optional[torch.Tensor] = None):
         st = None if mask is not None else self._rng_state(z.device)
@@ -111,6 +122,16 @@ class InnerProductDecoder(nn.Module):
         """Fused path: mean BCE-with-logits(z_d z_d^T, A, pos_weight) without the N x N arrays
         (replaces gae.py:71 + train_inductive.py:44,48).  per_graph=True restricts the pairs to
         each member graph of a batch (block-diagonal; an extension, not the reference default)."""
+        if z.shape[1] > ops.MAX_FUSED_DECODER_WIDTH:
+            # wider than the fused kernels go (the reference takes any --hidden_dims; its HPO script searches up
+            # to 256): the reference's own formulation -- materialised logits, dense adjacency, torch's BCE
+            if per_graph:
+                raise ops.GaeError(f"the per-graph decoder needs an embedding width <= {ops.MAX_FUSED_DECODER_WIDTH}")
+            adj = g.adjacency_matrix().to_dense().to(z.device)               # train_inductive.py:44
+            pw = torch.tensor(float(pos_weight), dtype=z.dtype, device=z.device)
+            st = None if mask is not None else self._rng_state(z.device)
+            logits = ops.DecoderLogitsFunction.apply(z, float(self.dropout), mask, st)
+            return F.binary_cross_entropy_with_logits(logits, adj, pos_weight=pw)           # :47-48
         st = None if mask is not None else self._rng_state(z.device)
         return ops.DecoderLossFunction.apply(z, g, float(pos_weight), float(self.dropout), mask, st, per_graph)
 
@@ -155,25 +176,36 @@ class GAE(nn.Module):
         by the embeddings (:53)."""
         z = self.encode(g)
         g.ndata['h'] = z
+        if lazy.ENABLED and z.is_cuda and self.decoder.activation is _IDENTITY:
+            # deferred logits: BCELoss(adj_logits, adj, pos_weight) on them is the fused decoder kernel; any
+            # other use materialises exactly what self.decoder(z) returns (same keep-mask)
+            return lazy.LazyLogits(z, lazy.keep_mask_for(self.decoder, z), g, self.decoder)
         return self.decoder(z)
 
     def loss(self, g, pos_weight: Optional[float] = None, mask: Optional[torch.Tensor] = None,
-             transductive: bool = False, per_graph: bool = False, fused_step: Optional[bool] = None):
+             transductive: bool = False, per_graph: bool = False, fused_step: Optional[bool] = None,
+             aggregated_input: bool = False):
         """Fused equivalent of `BCELoss(model.forward(g), adj, pos_weight)`
         (train_inductive.py:44-48), including the gae.py:53 write-back.
 
         fused_step (default: automatic) runs the whole step -- encoder, decoder loss and the
         backward -- behind ONE native call (ops.FusedStepFunction); it applies when every layer
         activation is ReLU / identity and the input features need no gradient.  The layer-by-layer
-        path (what `forward` / `encode` use) computes the same numbers."""
+        path (what `forward` / `encode` use) computes the same numbers.
+
+        aggregated_input=True: ndata['h'] already holds A X (ops.spmm of the input features, computed once by
+        the caller because features and graph do not change between epochs, train_transductive.py:45-46,63);
+        the first layer then skips its aggregation -- same bits, one 500-wide SpMM less per epoch."""
         if pos_weight is None:
             pos_weight = pos_weight_of(g, transductive, per_graph)
         x = g.ndata['h']
         codes = [_act_code(conv.apply_mod.activation) for conv in self.layers]
         can_fuse = all(c is not None for c in codes) and not x.requires_grad and \
-            self.layers[-1].apply_mod.linear.out_features <= 64 and len(self.layers) <= 8
+            self.layers[-1].apply_mod.linear.out_features <= ops.MAX_FUSED_DECODER_WIDTH and len(self.layers) <= 8
         if fused_step is None:
             fused_step = can_fuse
+        if aggregated_input and not fused_step:
+            raise ops.GaeError("aggregated_input needs the fused step (ReLU/identity activations, d_last <= 64)")
         if fused_step:
             if not can_fuse:
                 raise ops.GaeError("fused_step=True needs ReLU/identity activations, leaf features and d_last <= 64")
@@ -186,7 +218,7 @@ class GAE(nn.Module):
             st = None if mask is not None else self.decoder._rng_state(x.device)
             need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in params)
             loss, z = ops.FusedStepFunction.apply(x, g, dims, codes, float(pos_weight), float(self.decoder.dropout), mask,
-                                                  st, per_graph, need_grad, *params)
+                                                  st, (per_graph, aggregated_input), need_grad, *params)
             g.ndata['h'] = z
             return loss
         h = self.encode(g)

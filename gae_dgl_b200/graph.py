@@ -308,9 +308,17 @@ class DGLGraph:
             return ops.in_degrees(c.rowptr)
         return c.rowptr[1:] - c.rowptr[:-1]
 
-    def adjacency_matrix(self, transpose: bool = False) -> torch.Tensor:
-        """Sparse COO [N, N], rows = dst, cols = src, one 1.0 per edge; `.to_dense()` sums
-        duplicates (train_inductive.py:44)."""
+    def adjacency_matrix(self, transpose: bool = False):
+        """Sparse COO [N, N], rows = dst, cols = src, one 1.0 per edge; `.to_dense()` sums duplicates
+        (train_inductive.py:44).  On a CUDA graph the result is a handle whose `.to_dense()` is DEFERRED
+        (lazy.LazyAdjacency: the reference's `BCELoss(model.forward(g), adj, pos_weight)` then runs fused,
+        without any N x N array) and which otherwise behaves as the sparse tensor."""
+        from . import lazy
+        if lazy.ENABLED and self.csr().rowptr.is_cuda:
+            return lazy.AdjacencyHandle(self, transpose)
+        return self.adjacency_matrix_sparse(transpose)
+
+    def adjacency_matrix_sparse(self, transpose: bool = False) -> torch.Tensor:
         c = self.csr()
         deg = c.rowptr[1:] - c.rowptr[:-1]
         rows = torch.repeat_interleave(torch.arange(self._n, device=c.rowptr.device), deg)
@@ -473,6 +481,7 @@ class PackedGraphDataset:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise GaeError("PackedGraphDataset lives on a CUDA device")
+        torch.cuda.set_device(self.device)     # its batches are assembled by native kernels on the current device
         self.feature_key = feature_key
         self.n_graphs = len(graphs)
         nodes = np.asarray([g.number_of_nodes() for g in graphs], dtype=np.int64)

@@ -21,6 +21,7 @@ ACT_RELU = 1
 DEC_LOSS = 1
 DEC_GRAD = 2
 DEFAULT_SEG_LEN = 512
+MAX_FUSED_DECODER_WIDTH = 64      # dec_config (csrc/decoder.cu): wider embeddings take the materialised path
 
 
 # ------------------------------------------------------------------------------------------
@@ -49,6 +50,12 @@ def _require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
                        f"{type(t).__name__} on {getattr(t, 'device', None)}")
     if t.dtype != dtype:
         raise GaeError(f"{name} must be {dtype}, got {t.dtype}")
+    # the library launches on the CURRENT device and stream: a tensor that lives elsewhere would be an
+    # illegal access (or, with peer access enabled, a silent race against that device's stream)
+    cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+    if t.device.index != cur:
+        raise GaeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{cur}; call "
+                       f"torch.cuda.set_device({t.device.index}) (the trainers do) or wrap the call in torch.cuda.device(...)")
 
 
 def round_up4(d: int) -> int:
@@ -456,6 +463,9 @@ class FusedStepFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, graph, dims, acts, pos_weight, p, mask, rng_state, per_graph, need_grad, *params):
+        x_aggregated = False
+        if isinstance(per_graph, tuple):              # (per_graph, x_aggregated): keeps the positional signature
+            per_graph, x_aggregated = per_graph
         from ._lib import StepDesc
         lib = _lib.load()
         X = as_rows(X, "features")
@@ -469,6 +479,7 @@ class FusedStepFunction(torch.autograd.Function):
         for i, a in enumerate(acts):
             desc.acts[i] = int(a)
         desc.dropout_p, desc.pos_weight, desc.per_graph = float(p), float(pos_weight), int(bool(per_graph))
+        desc.x_aggregated = int(bool(x_aggregated))
         Ws = [params[2 * l].contiguous() for l in range(L)]
         bs = [params[2 * l + 1].contiguous() for l in range(L)]
         want_grad = bool(need_grad)
@@ -508,6 +519,6 @@ class FusedStepFunction(torch.autograd.Function):
     def backward(ctx, g_loss, _g_z):
         if ctx.grads is None:
             return (None,) * 10
-        grads = ctx.grads
-        torch._foreach_mul_(grads, g_loss)
-        return (None,) * 10 + tuple(grads)
+        # out of place: the cached unit gradients stay valid for a second backward (retain_graph) and never
+        # alias what autograd installs as .grad
+        return (None,) * 10 + tuple(torch._foreach_mul(ctx.grads, g_loss))

@@ -55,13 +55,17 @@ def build_parser():
 def get_device(gpu_id: int) -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("gae_dgl_b200 needs a CUDA device (B200); there is no CPU path")
-    return torch.device("cuda:{}".format(gpu_id))
+    device = torch.device("cuda:{}".format(gpu_id))
+    torch.cuda.set_device(device)          # the native kernels launch on the current device and its stream
+    return device
 
 
 class Trainer:
     def __init__(self, model, args, device=None):
         self.model = model
         self.device = device if device is not None else next(model.parameters()).device
+        if self.device.type == 'cuda':
+            torch.cuda.set_device(self.device)
         self.optim = torch.optim.Adam(self.model.parameters(), lr=args.lr, fused=self.device.type == 'cuda')
         self.dense = bool(getattr(args, 'dense_decoder', False))
         self.per_graph = bool(getattr(args, 'per_graph_decoder', False))
@@ -103,7 +107,8 @@ class Trainer:
         torch.save(self.model.state_dict(), output_path)     # reference format (train_inductive.py:55-57)
         if self.native is not None:
             self.native.sync_state()
-        torch.save({'epoch': epoch, 'model': self.model.state_dict(), 'optim': self.optim.state_dict()},
+        torch.save({'epoch': epoch, 'model': self.model.state_dict(), 'optim': self.optim.state_dict(),
+                    'decoder_rng': self.model.decoder.rng_state_dict()},       # the dropout stream resumes too
                    os.path.join(save_dir, 'ep{:02}.ckpt'.format(epoch)))
         return output_path
 
@@ -113,10 +118,15 @@ class Trainer:
         if isinstance(st, dict) and 'model' in st and 'optim' in st:
             self.model.load_state_dict(st['model'])
             self.optim.load_state_dict(st['optim'])
+            self.model.decoder.load_rng_state(st.get('decoder_rng'), self.device)
             self._make_native()                  # the optimiser state tensors were replaced
             return int(st.get('epoch', -1)) + 1
         self.model.load_state_dict(st)
-        return 0
+        # a bare reference checkpoint 'epNN.pkl' (train_inductive.py:55-57) carries its epoch in the file name:
+        # resume after it instead of overwriting the earlier checkpoints from epoch 0
+        import re
+        m = re.fullmatch(r'ep(\d+)\.pkl', os.path.basename(str(path)))
+        return int(m.group(1)) + 1 if m else 0
 
 
 def make_collate(device):

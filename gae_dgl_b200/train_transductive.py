@@ -21,6 +21,7 @@ import numpy as np
 import torch
 from torch.nn.functional import binary_cross_entropy_with_logits as BCELoss
 
+from . import ops
 from .data import find_planetoid, load_data as load_planetoid_data, register_data_args
 from .gae import GAE, VGAE, pos_weight_of
 from .graph import DGLGraph
@@ -42,6 +43,8 @@ def build_parser():
     parser.add_argument('--dense_decoder', action='store_true', help="reference's materialised N x N loss")
     parser.add_argument('--log_every', type=int, default=50)
     parser.add_argument('--no_cuda_graph', action='store_true', help='run every epoch eagerly')
+    parser.add_argument('--no_hoist', action='store_true',
+                        help='aggregate the (constant) input features every epoch like the reference does')
     return parser
 
 
@@ -80,10 +83,20 @@ def train(args, features, g, device, verbose=True):
         adj = g.adjacency_matrix().to_dense()
         pw_t = torch.tensor([pos_weight], device=device)
 
+    # Loop invariant of :45-46,63: features and graph never change, so the first layer's aggregation A X is
+    # the same every epoch.  It is computed once (same kernel, same bits) and the fused step starts from it.
+    hoist = not args.dense_decoder and not args.variational and not getattr(args, 'no_hoist', False) and \
+        args.hidden_dims[-1] <= 64
+    agg_features = ops.spmm(g.csr().rowptr, g.csr().col, ops.as_rows(features, "features"), g.csr().plan) if hoist else None
+
     def loss_fn():
-        g.ndata['h'] = features                     # repaired :46 / gae.py:53 overwrite
         if args.dense_decoder:
+            g.ndata['h'] = features                 # repaired :46 / gae.py:53 overwrite
             return BCELoss(model.forward(g), adj, pos_weight=pw_t)
+        if hoist:
+            g.ndata['h'] = agg_features
+            return model.loss(g, pos_weight=pos_weight, aggregated_input=True)
+        g.ndata['h'] = features
         return model.loss(g, pos_weight=pos_weight)
 
     losses = []
@@ -123,6 +136,7 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise RuntimeError("gae_dgl_b200 needs a CUDA device (B200); there is no CPU path")
     device = torch.device("cuda:{}".format(args.gpu_id))
+    torch.cuda.set_device(device)          # the native kernels launch on the current device and its stream
     if args.seed is not None:
         torch.manual_seed(args.seed)
     os.makedirs(args.save_dir, exist_ok=True)

@@ -204,6 +204,9 @@ typedef struct gae_step_desc_t {
     float dropout_p;                    /* decoder dropout, gae.py:64                    */
     float pos_weight;                   /* train_inductive.py:46                         */
     int32_t per_graph;                  /* 0 = full N x N pairs (reference), 1 = block-diagonal */
+    int32_t x_aggregated;               /* 1 = X already holds A X (the caller aggregated the input features
+                                         * once: they and the graph are fixed across the epochs of
+                                         * train_transductive.py:45-46,63); the first SpMM is skipped        */
 } gae_step_desc_t;
 int64_t gae_step_ws_bytes(const gae_step_desc_t *desc, int64_t n, const gae_hub_plan_t *plan,
                           const gae_hub_plan_t *plan_t);

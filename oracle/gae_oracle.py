@@ -244,6 +244,72 @@ def train_step(rowptr, col, X, weights, keep_mask, p=0.1, transductive=False, dt
     return loss.detach(), z.detach(), grads
 
 
+def _decoder_loss_blocked_backward(zd: torch.Tensor, rowptr, col, pos_weight: float, block: int = 2048):
+    """Value of bce_loss_sparse_form and its gradient w.r.t. zd, the dense N x N term evaluated in row
+    blocks of `block` (the N = 19 717 Pubmed step does not fit a dense fp64 autograd graph comfortably:
+    N^2 = 3.9e8 elements per temporary).  Same arithmetic as bce_loss_sparse_form, block by block."""
+    n = zd.shape[0]
+    leaf = zd.detach().clone().requires_grad_(True)
+    total = 0.0
+    for lo in range(0, n, block):
+        l_b = softplus(leaf[lo:lo + block] @ leaf.t()).sum() / float(n * n)
+        l_b.backward()
+        total += float(l_b.detach())
+    deg = rowptr[1:] - rowptr[:-1]
+    i = torch.repeat_interleave(torch.arange(n, dtype=torch.int64), deg)
+    j = col.to(torch.int64)
+    xe = (leaf[i] * leaf[j]).sum(1)
+    l_s = (pos_weight * softplus(-xe) - softplus(xe)).sum() / float(n * n)
+    l_s.backward()
+    return total + float(l_s.detach()), leaf.grad
+
+
+def train_step_blocked(rowptr, col, X, weights, keep_mask, p=0.1, transductive=False, dtype=torch.float64,
+                       block: int = 2048):
+    """train_step (train_inductive.py:44-51) without any N x N array: the decoder loss in its closed form
+    (bce_loss_sparse_form, exact for multigraph targets), dense term in row blocks.  Pinned against
+    train_step -- which executes the cited lines literally -- in tests/test_oracle_pins.py."""
+    ws = [(W.detach().to(dtype).clone().requires_grad_(True), b.detach().to(dtype).clone().requires_grad_(True))
+          for W, b in weights]
+    n = rowptr.numel() - 1
+
+    class _Adj:      # what pos_weight_* read of the dense adjacency: its shape and its (fp32, exact < 2^24) sum
+        shape = (n, n)
+
+        @staticmethod
+        def sum():
+            return torch.tensor(float(col.numel()), dtype=torch.float32)
+
+    pw = float(pos_weight_transductive(_Adj) if transductive else pos_weight_inductive(_Adj))
+    z = encode(rowptr, col, X.to(dtype), ws)
+    zd = apply_dropout_mask(z, keep_mask, p)
+    loss, g_zd = _decoder_loss_blocked_backward(zd, rowptr, col, pw, block)
+    zd.backward(g_zd)
+    grads = [(W.grad.clone(), b.grad.clone()) for W, b in ws]
+    return torch.tensor(loss, dtype=dtype), z.detach(), grads
+
+
+def vgae_train_step(rowptr, col, X, trunk, mu_head, logstd_head, eps, keep_mask, p=0.1, transductive=False,
+                    dtype=torch.float64):
+    """fp64 restatement of the VGAE step (Kipf & Welling 2016; the reference has no VGAE code, README.md:58
+    cites the paper -- the module under test defines the architecture: shared GCN trunk with ReLU, two
+    identity GCN heads, z = mu + eps * exp(logstd), the GAE decoder and loss lines (gae.py:69-72,
+    train_inductive.py:44-48) plus vgae_kl).  Returns (loss, mu, logstd, grads of [trunk..., mu, logstd])."""
+    mk = lambda W, b: (W.detach().to(dtype).clone().requires_grad_(True), b.detach().to(dtype).clone().requires_grad_(True))  # noqa: E731
+    ws = [mk(W, b) for W, b in list(trunk) + [mu_head, logstd_head]]
+    h = X.to(dtype)
+    for W, b in ws[:-2]:
+        h = gcn_layer(rowptr, col, h, W, b, relu=True)
+    mu = gcn_layer(rowptr, col, h, ws[-2][0], ws[-2][1], relu=False)
+    logstd = gcn_layer(rowptr, col, h, ws[-1][0], ws[-1][1], relu=False)
+    z = mu + eps.to(dtype) * torch.exp(logstd)
+    adj = dense_adj_from_csr(rowptr, col, dtype=dtype)
+    pw = pos_weight_transductive(adj.float()) if transductive else pos_weight_inductive(adj.float())
+    loss = bce_loss(decoder_logits(z, keep_mask, p), adj, pw.to(dtype)) + vgae_kl(mu, logstd)
+    loss.backward()
+    return loss.detach(), mu.detach(), logstd.detach(), [(W.grad.clone(), b.grad.clone()) for W, b in ws]
+
+
 # --------------------------------------------------------------------------------------
 # Module-shaped oracle (same constructor / state_dict keys as gae.py) so that parity
 # tests read like tests of the reference module.

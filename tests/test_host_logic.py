@@ -236,7 +236,7 @@ def test_link_prediction_eval_utility():
 
 def test_step_desc_matches_header(lib_built):
     """ctypes mirrors of the C structs have the sizes the header implies."""
-    assert ctypes.sizeof(_lib.StepDesc) == 4 + 4 * 9 + 4 * 8 + 4 + 4 + 4
+    assert ctypes.sizeof(_lib.StepDesc) == 4 + 4 * 9 + 4 * 8 + 4 + 4 + 4 + 4
     assert ctypes.sizeof(_lib.HubPlanStruct) == 4 + 4 + 8 + 8 + 8 * 3 + 8 * 3 + 8 * 3 + 8
     lib = _lib.load()
     d = _lib.StepDesc()
@@ -247,6 +247,8 @@ def test_step_desc_matches_header(lib_built):
     a = lib.gae_step_ws_bytes(ctypes.byref(d), 1000, None, None)
     b = lib.gae_step_ws_bytes(ctypes.byref(d), 2000, None, None)
     assert 0 < a < b
+    d.x_aggregated = 1                      # the caller brings A X: no buffer for the first aggregation
+    assert lib.gae_step_ws_bytes(ctypes.byref(d), 1000, None, None) < a
 
 
 def _write_planetoid(directory, name, n_train, n_all, test_ids, n_feat, n_cls, adj_lists, seed=0):

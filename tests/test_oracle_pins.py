@@ -58,6 +58,29 @@ def test_pin_sparse_form_identity_and_gradient():
     assert torch.allclose(g1, (G + G.t()) @ z.detach(), rtol=1e-9, atol=1e-13)
 
 
+def test_pin_blocked_train_step_equals_the_literal_one():
+    """train_step_blocked (no N x N array; what the Pubmed-size GPU parity test uses) against train_step, which
+    executes train_inductive.py:44-51 literally -- several row blocks, duplicate edges, both pos_weight forms."""
+    g = torch.Generator().manual_seed(5)
+    n, e, f = 157, 900, 23
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    src, dst = torch.cat([src, src[:40]]), torch.cat([dst, dst[:40]])
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    X = torch.randn(n, f, generator=g)
+    torch.manual_seed(3)
+    ref = O.OracleGAE(f, [12, 8])
+    weights = [(l.apply_mod.linear.weight.detach(), l.apply_mod.linear.bias.detach()) for l in ref.layers]
+    mask = torch.rand(n, 8, generator=g) >= 0.1
+    for transductive in (False, True):
+        l0, z0, g0 = O.train_step(rowptr, col, X, weights, mask, transductive=transductive, dtype=torch.float64)
+        l1, z1, g1 = O.train_step_blocked(rowptr, col, X, weights, mask, transductive=transductive, block=50)
+        assert abs(float(l0) - float(l1)) < 1e-6 * abs(float(l0))        # pos_weight is an fp32 value in both
+        assert torch.equal(z0, z1)
+        for (a, b), (c, d) in zip(g0, g1):
+            assert float((a - c).abs().max()) < 1e-9 * max(float(a.abs().max()), 1.0)
+            assert float((b - d).abs().max()) < 1e-9 * max(float(b.abs().max()), 1.0)
+
+
 def test_pin_linear_init_and_param_counts():
     # pins (4), (5)
     lin = nn.Linear(39, 32)
