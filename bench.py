@@ -225,17 +225,17 @@ def cpu_rmat_leg(scale: int, n_edges: int, budget_s: float, max_steps: int = 10)
     }
 
 
-def cpu_pubmed_leg(steps: int = 2):
-    """Reference train step on the Pubmed-shaped graph on the host: dense adj, encoder, dropout,
-    Z Z^T, weighted BCE, backward, Adam (train_transductive.py:55-68 repaired)."""
+def cpu_pubmed_leg(steps: int = 2, name: str = "pubmed"):
+    """Reference train step on the Pubmed- (configs[1]) or Cora-shaped (configs[0]) graph on the host: dense adj,
+    encoder, dropout, Z Z^T, weighted BCE, backward, Adam (train_transductive.py:55-68 repaired)."""
     from gae_dgl_b200 import synthetic
     from oracle import gae_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g, X = synthetic.planetoid_like("pubmed", seed=0)
+    g, X = synthetic.planetoid_like(name, seed=0)
     c = g.csr()
     torch.manual_seed(0)
-    model = O.OracleGAE(500, [32, 16])
+    model = O.OracleGAE(X.shape[1], [32, 16])
     opt = torch.optim.Adam(model.parameters(), lr=1e-2)
     ts = []
     for _ in range(steps):
@@ -250,7 +250,8 @@ def cpu_pubmed_leg(steps: int = 2):
         ts.append(time.perf_counter() - t0)
     t = min(ts)
     return {"value": g.number_of_edges() / t, "unit": "edges/s", "cores": cores, "kind": "port",
-            "sample": f"full Pubmed-shaped train step, best of {steps}", "ms_per_step": t * 1e3}
+            "sample": f"full {name.capitalize()}-shaped train step (N={g.number_of_nodes()}, E={g.number_of_edges()}, "
+                      f"F={X.shape[1]}), best of {steps}", "ms_per_step": t * 1e3}
 
 
 # ------------------------------------------------------------------------------------------
@@ -278,6 +279,7 @@ def run_reference(args):
         "variants_ms": leg["variants_ms"],
     }
     if not args.no_pubmed and n_gpus == 1 and not args.strong:
+        line["cora"] = cpu_pubmed_leg(steps=5, name="cora")      # configs[0]: the reference's CPU-runnable case
         line["pubmed"] = cpu_pubmed_leg()
         line["zinc"] = cpu_zinc_leg()
     print(json.dumps(line), flush=True)
@@ -329,22 +331,71 @@ def cuda_time_ms(fn, steps, stream):
     return e0.elapsed_time(e1)
 
 
-def pubmed_leg(dev, steps=100, warmup=5):
+def decoder_roofline(dev, g, d=16, iters=20):
+    """Roofline of the dominant kernel of the small-graph train steps: the fused decoder (dense pass over all
+    N^2 pairs + finalize), timed ALONE with CUDA events on its launching stream.  Algorithmic work per launch
+    (DESIGN.md K5/K6): 4 N^2 d flop (S = Zd Zd^T and dZ = sigma(S) Zd; the reference's mm + BCE + backward do
+    more) and 2 N^2 MUFU ops (ex2 + rcp per pair; lg2 folded 64:1).  `bound` is "tensor": peak = half the
+    MEASURED bf16 rate (TF32 runs at half the bf16 rate; split precision triples the issued MMAs, which the
+    algorithmic count deliberately ignores).  The MUFU floor (16 ops/clk/SM x 148 SMs x max SM clock) is
+    reported beside it -- for d = 16 it is the tighter of the two."""
+    from gae_dgl_b200 import ops
+    n = g.number_of_nodes()
+    c, t = g.csr(), g.csr_t()
+    Zd = torch.randn(n, d, device=dev) * 0.3
+    pw = 5.0
+    st = torch.cuda.current_stream()
+
+    def fn():
+        ops.decoder_bce(Zd, c.rowptr, c.col, t.rowptr, t.col, pw, want_loss=True, want_grad=True)
+
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ms = cuda_time_ms(fn, iters, st) / iters
+    flops = 4.0 * n * n * d
+    pk = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+    bf16 = float(pk.get("bf16_tflops", 1590.0))
+    sm_mhz = float(pk.get("sm_max_mhz", 1965.0))
+    peak = 0.5 * bf16
+    mufu_floor_ms = 2.0 * n * n / (16 * 148 * sm_mhz * 1e6) * 1e3
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "kernel": "gae_decoder_bce_f32 (dense pass + finalize + loss reduce), timed alone", "ms": ms,
+            "algorithmic_flops": flops, "mufu_ops": 2.0 * n * n, "mufu_floor_ms": mufu_floor_ms,
+            "frac_mufu": mufu_floor_ms / ms,
+            "peak_source": ("0.5 x measured bf16 burst (MEASURED_PEAKS.json)" if pk else "0.5 x fallback bf16 1.59 PF")}
+
+
+def pubmed_leg(dev, steps=100, warmup=5, name="pubmed"):
     """configs[1]: Pubmed-shaped transductive train step (fwd + bwd + Adam, fused decoder), as
     train_transductive.py runs it: the step captured in a CUDA graph and replayed."""
     import gae_dgl_b200 as G
     from gae_dgl_b200 import synthetic
     from gae_dgl_b200.graphed import GraphedTrainStep
-    g, X = synthetic.planetoid_like("pubmed", seed=0)
+    g, X = synthetic.planetoid_like(name, seed=0)
     torch.manual_seed(0)
-    model = G.GAE(500, [32, 16]).to(dev)
+    model = G.GAE(X.shape[1], [32, 16]).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True, fused=True)
     g.to(dev)
     Xd = X.to(dev)
     pw = G.pos_weight_of(g, transductive=True)
     st = torch.cuda.current_stream()
+    from gae_dgl_b200 import ops
+    # as train_transductive.py runs it: the first layer's A X is loop-invariant and computed once per change of
+    # the features (bit-identical); in the e2e variant the features arrive from the host EVERY step, so there
+    # the aggregation is part of the step again
+    agg = ops.spmm(g.csr().rowptr, g.csr().col, Xd, g.csr().plan)
 
     def loss_fn():
+        g.ndata["h"] = agg
+        return model.loss(g, pos_weight=pw, aggregated_input=True)
+
+    def loss_fn_e2e():
         g.ndata["h"] = Xd
         return model.loss(g, pos_weight=pw)
 
@@ -355,10 +406,11 @@ def pubmed_leg(dev, steps=100, warmup=5):
     ms = cuda_time_ms(step, steps, st) / steps
     # e2e: features from pinned host memory every step, loss read back every step
     Xp = X.pin_memory()
+    step2 = GraphedTrainStep(model, opt, loss_fn_e2e, warmup=warmup)
 
     def step_e2e():
         Xd.copy_(Xp, non_blocking=True)
-        return step().item()
+        return step2().item()
 
     step_e2e()
     torch.cuda.synchronize()
@@ -368,45 +420,57 @@ def pubmed_leg(dev, steps=100, warmup=5):
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
     e = g.number_of_edges()
-    return {"workload": "pubmed_like_N19717_E88651_F500 train step (fwd+bwd+Adam, fused decoder, CUDA-graph replay)",
+    return {"workload": f"{name}_like_N{g.number_of_nodes()}_E{e}_F{X.shape[1]} train step (fwd+bwd+Adam, fused decoder, "
+                        "CUDA-graph replay, input aggregation hoisted out of the epoch loop)",
             "value": e / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "final_loss": last,
+            "roofline": decoder_roofline(dev, g),
             "e2e": {"value": e / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(X.numel() * 4), "d2h_bytes_per_step": 4}}
 
 
 def zinc_leg(dev, steps=60, warmup=5, batch_size=256):
-    """configs[2]: ZINC-shaped inductive step, batch = 256 molecules, hidden 32/16: device collation
-    from the packed dataset + fused native step + Adam, a new random batch every step."""
+    """configs[2]: ZINC-shaped inductive step, batch = 256 molecules, hidden 32/16, as train_inductive.py runs it:
+    device collation from the packed dataset + the native train step (gae_step_fwd_bwd_f32 + gae_adam_step_f32),
+    a new random batch every step.  `value`: losses stay on the device (one sync at the end); `e2e`: the batch's
+    molecule ids come from pinned host memory and the loss is read back EVERY step (train_inductive.py:53)."""
     import gae_dgl_b200 as G
     from gae_dgl_b200 import synthetic
     from gae_dgl_b200.graph import PackedGraphDataset
+    from gae_dgl_b200.native_step import NativeTrainStep
     ds = synthetic.zinc_like_dataset(4096, seed=0)
     packed = PackedGraphDataset(ds, dev)
     torch.manual_seed(0)
     model = G.GAE(39, [32, 16]).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    native = NativeTrainStep(model, opt)
     rng = np.random.default_rng(0)
-    batches = [rng.permutation(len(ds))[:batch_size] for _ in range(steps + warmup)]
+    batches = [rng.permutation(len(ds))[:batch_size] for _ in range(2 * steps + warmup)]
     edges = float(np.mean([packed.edges[b].sum() for b in batches[warmup:]]))
 
     def step(ids):
-        loss = model.loss(packed.batch(ids))
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+        return native(packed.batch(ids))
 
     for ids in batches[:warmup]:
         step(ids)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for ids in batches[warmup:]:
+    for ids in batches[warmup:warmup + steps]:
         last = step(ids)
     last = float(last)                       # one sync at the end; includes host collation cost
     ms = (time.perf_counter() - t0) * 1e3 / steps
+    t0 = time.perf_counter()
+    for ids in batches[warmup + steps:]:
+        last_e2e = float(step(ids))          # device -> host read of the loss every step
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    big = G.batch(ds[:batch_size], device=dev)
     return {"workload": f"zinc_like batch={batch_size} (mean {edges:.0f} directed edges/batch) inductive train step: "
-                        "device collation + fwd + bwd + Adam, wall clock incl. host overhead",
-            "value": edges / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "final_loss": last}
+                        "device collation + native fwd/bwd + native Adam, wall clock incl. host overhead",
+            "value": edges / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms, "final_loss": last,
+            "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(batch_size * 8 + 2 * (batch_size + 1) * 8), "d2h_bytes_per_step": 4,
+                    "final_loss": last_e2e,
+                    "api": "PackedGraphDataset.batch(host ids) + NativeTrainStep; loss.item() every step"},
+            "roofline": decoder_roofline(dev, big)}
 
 
 def cpu_zinc_leg(steps=2, batch_size=256):
@@ -609,7 +673,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         leg = cpu_rmat_leg(scale, total_edges, min(args.cpu_seconds, 20.0), max_steps=5)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        if not args.no_pubmed:
+        if not args.no_pubmed and not args.strong:
+            line["cora"] = pubmed_leg(dev, name="cora")           # configs[0] (CPU-runnable reference case) beside its CPU time
+            line["cora"]["cpu_baseline"] = cpu_pubmed_leg(steps=5, name="cora")
             line["pubmed"] = pubmed_leg(dev)
             line["pubmed"]["cpu_baseline"] = cpu_pubmed_leg()
             line["zinc"] = zinc_leg(dev)
