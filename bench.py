@@ -612,7 +612,8 @@ def run_ours(args):
     achieved = alg_bytes / (statistics.mean(fwd_ms) * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath) and world == 1:      # an ncu capture of the single-GPU C4 launch; means nothing at N > 1
+    if os.path.exists(tpath) and world == 1 and (scale, total_edges) == (22, 100_000_000):
+        # an ncu capture of the single-GPU C4 launch (profiles/): means nothing for any other workload
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
