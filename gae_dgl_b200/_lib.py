@@ -128,6 +128,8 @@ SIGNATURES = {
     "gae_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8 * 64), POINTER(c_int64)]),
     "gae_ipc_open_handle": (c_int, [POINTER(c_uint8 * 64), POINTER(c_void_p)]),
     "gae_ipc_close_handle": (c_int, [c_void_p]),
+    "gae_decoder_tile_probe_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                           c_void_p, POINTER(c_int32), c_void_p]),
     "gae_halo_push_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_void_p]),
     "gae_halo_push_range_f32": (c_int, [POINTER(HaloExchangeStruct), c_uint64, c_int32, c_int32, c_void_p]),
     "gae_halo_wait_f32": (c_int, [POINTER(HaloExchangeStruct), c_int32, c_uint64, c_void_p]),

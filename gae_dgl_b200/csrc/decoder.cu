@@ -28,7 +28,14 @@ struct DecConfig {
     int64_t j_chunk;   // key rows per split
     int64_t fin_blocks;
     bool mma;          // D = 16: both GEMMs on the tensor cores (dec_dense_mma_kernel)
+    bool tc;           // D = 16: tcgen05 / TMEM symmetric-half pass (decoder_tc.cu); nb = 128-row blocks then
 };
+
+// decoder_tc.cu
+int dec_tc_splits(int64_t n);
+cudaError_t dec_tc_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
+                          double *loss_part, uint32_t *err, cudaStream_t st);
+constexpr int64_t DEC_TC_MIN_ROWS = 512;
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (d <= 16) { c->D = 16; c->R = tuning(T_DEC_ROWS) == 1 ? 1 : 2; }
@@ -36,6 +43,16 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     else if (d <= 64) { c->D = 64; c->R = 1; }
     else return false;
     c->mma = d <= 16 && tuning(T_DEC_MMA) != 0;
+    c->tc = d <= 16 && tuning(T_DEC_TC) != 0 && n >= DEC_TC_MIN_ROWS;
+    if (c->tc) {
+        c->mma = false;
+        c->JT = 128;
+        c->nb = cdiv(n, 128);
+        c->splits = dec_tc_splits(n);
+        c->j_chunk = 0;
+        c->fin_blocks = cdiv(n, 256 / (c->D / 4));
+        return true;
+    }
     // query rows per CTA: the tensor-core kernel covers 4 warps x 2 m-tiles x 16 rows
     const int64_t rows_pb = c->mma ? 128 : (int64_t)DEC_THREADS * c->R;
     c->JT = 2048 / c->D;
@@ -407,7 +424,8 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
                     const int64_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t, float pw,
                     const float *__restrict__ dz_part, int splits, int mode, float inv_n2,
                     float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part,
-                    const int64_t *__restrict__ blk_lo, const int64_t *__restrict__ blk_hi) {
+                    const int64_t *__restrict__ blk_lo, const int64_t *__restrict__ blk_hi,
+                    const float *__restrict__ dzT_part = nullptr) {
     constexpr int LPR = D / 4;
     constexpr int RPB = 256 / LPR;
     __shared__ double red[8];
@@ -439,6 +457,10 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
     if (want_grad && valid && !blk_lo) {
         for (int s = 0; s < splits; ++s)
             f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
+        // symmetric-half pass: the tiles (I, block of i), I < block, delivered sigma^T Z_I in slot I
+        if (dzT_part)
+            for (int64_t I = 0; I < i / 128; ++I)
+                f4_add(g, *reinterpret_cast<const float4 *>(dzT_part + (I * n + i) * D + sub * 4));
         // x_ij = x_ji: (G + G^T) Zd doubles the dense term
         g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
     }
@@ -608,7 +630,8 @@ extern "C" int64_t gae_decoder_ws_bytes(int64_t n, int32_t d) {
     if (n <= 0 || d <= 0 || !dec_config(n, d, &c)) return 0;
     const int64_t dz = align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256);
     const int64_t lp = (int64_t)sizeof(double) * (c.nb * c.splits + c.fin_blocks);
-    return dz + align_up(lp, 256);
+    const int64_t tc = c.tc ? align_up((int64_t)sizeof(float) * c.nb * n * c.D, 256) + 256 : 0;
+    return dz + align_up(lp, 256) + tc;
 }
 
 extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d,
@@ -637,7 +660,14 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     float *dz_part = (float *)ws;
     double *loss_part = (double *)((char *)ws + align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256));
     double *loss_part_edges = loss_part + c.nb * c.splits;
-
+    float *dzT_part = nullptr;
+    if (c.tc) {
+        char *p = (char *)loss_part + align_up((int64_t)sizeof(double) * (c.nb * c.splits + c.fin_blocks), 256);
+        uint32_t *err = (uint32_t *)p;
+        dzT_part = (float *)(p + 256);
+        GAE_CUDA(cudaMemsetAsync(err, 0, sizeof(uint32_t), st));
+        GAE_CUDA(dec_tc_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
+    } else
     if (c.mma) GAE_CUDA(launch_dense_mma(c, mode, Zd, ldz, n, d, dz_part, loss_part, st));
     else if (c.D == 16 && c.R == 1) GAE_CUDA((launch_dense<16, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
     else if (c.D == 16) GAE_CUDA((launch_dense<16, 2>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
@@ -648,7 +678,7 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     if (c.D == 16)
         dec_finalize_kernel<16><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
                                                                         dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
-                                                                        nullptr, nullptr);
+                                                                        nullptr, nullptr, dzT_part);
     else if (c.D == 32)
         dec_finalize_kernel<32><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
                                                                         dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,

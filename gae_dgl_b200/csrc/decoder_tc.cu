@@ -1,0 +1,430 @@
+// K5 / K6 on the 5th-generation tensor cores: the dense pass of the fused decoder for d <= 16,
+// over the UPPER TRIANGLE of 128 x 128 tiles only.
+//
+// Reference: logits = mm(zd, zd.t()) (gae.py:71) + BCEWithLogits and its backward
+// (train_inductive.py:44-51).  X = Zd Zd^T is symmetric whatever the graph is, so a tile (I, J), I < J,
+// is evaluated ONCE and feeds both row blocks:
+//     S      = Z_I Z_J^T                       128 x 128 logits        (tcgen05.mma, accumulator in TMEM)
+//     sigma  = sigmoid(S), loss += 2 softplus(S)                       (tcgen05.ld -> registers, MUFU chain)
+//     G_I   += sigma   Z_J    (rows of block I)                        (tcgen05.mma, sigma from shared memory)
+//     G_J    = sigma^T Z_I    (rows of block J, one partial per I)     (tcgen05.mma, the SAME sigma tile read
+//                                                                       M-major through its descriptor)
+// Diagonal tiles contribute once and skip G_J.  That halves the S GEMM and -- the actual bound for d = 16 --
+// the ex2 + rcp chain: 2 MUFU ops per pair at 16 per clock per SM.
+//
+// Precision: operands are split hi + lo (hi = TF32 rounding, lo = remainder) and every product is
+// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (~2^-21 relative), the scheme of the mma.sync kernel
+// this replaces, under the same 1e-5 parity tests.  Gradient accumulators leave TMEM after every tile and
+// are summed in fp32 registers (tensor-core accumulation truncates; chains stay 128 keys long).
+//
+// Shared-memory operand layout: the no-swizzle canonical form, 8 x 16-byte core matrices.  A tile stored as
+//     off(r, c) = (r / 8) * SBO + (c / 4) * 128 + (r % 8) * 16 + (c % 4) * 4
+// is K-major for a product contracting over c (LBO = 128, SBO) and MN-major for one contracting over r
+// (SBO' = 128, LBO' = SBO): Z tiles (SBO = 512) serve as A/B of S and as B of both gradient products,
+// the sigma tile (SBO = 4096) as A of G_I (K-major) and as A of G_J (MN-major) -- no transposed copies.
+//
+// One CTA (256 threads, 1 per SM: 160 KB of shared memory) walks a run of tiles J of one row block I.
+// Thread 0 issues every MMA; completion comes back through tcgen05.commit on an mbarrier; all eight warps
+// run the element-wise chain (warp w: TMEM lanes 32 (w % 4).., columns 64 (w / 4)..).  Deterministic: the
+// G_I partial of CTA (I, s) and the G_J partial of tile (I, J) have their own slots, summed in fixed order by
+// dec_finalize_kernel.  Spin loops are bounded (%globaltimer): on expiry an error word is set and the kernel
+// falls through, so a protocol fault yields a reported error, never a hung GPU.
+#include "common.cuh"
+
+namespace gae {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_TILE = 128;
+constexpr int TC_D = 16;
+constexpr uint32_t TC_TMEM_COLS = 256;   // S: 128 | G_I: 16 | G_J: 16 (power of two >= 160)
+constexpr uint32_t TC_COL_S = 0, TC_COL_GI = 128, TC_COL_GJ = 144;
+constexpr int TC_Z_BYTES = TC_TILE * TC_D * 4;        // 8 KB
+constexpr int TC_SG_BYTES = TC_TILE * TC_TILE * 4;    // 64 KB
+constexpr int TC_OFF_ZI_HI = 0, TC_OFF_ZI_LO = TC_Z_BYTES, TC_OFF_ZJ_HI = 2 * TC_Z_BYTES, TC_OFF_ZJ_LO = 3 * TC_Z_BYTES;
+constexpr int TC_OFF_SG_HI = 4 * TC_Z_BYTES, TC_OFF_SG_LO = TC_OFF_SG_HI + TC_SG_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_SG_LO + TC_SG_BYTES;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 64;
+
+struct TcArgs {
+    const float *Zd;
+    int64_t ldz, n;
+    int32_t d, T, splits;
+    float *dz_part;       // [splits][n][16]: G_I partial of CTA (I, s)
+    float *dzT_part;      // [T][n][16]: G_J partial of tile (I, J) at slot I, rows of block J
+    double *loss_part;    // [T * splits]
+    uint32_t *err;        // bounded-wait expiry counter
+    // probe (one tile, one CTA): raw S, G_I, G_J
+    float *probe_S, *probe_GI, *probe_GJ;
+    int32_t probe_I, probe_J;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), LBO >> 4 at
+// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64))
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t tc_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded wait on an mbarrier phase
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t *err) {
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if ((it & 255u) == 255u) {
+            const uint64_t now = tc_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) {   // 2 s
+                atomicAdd(err, 1u);
+                break;
+            }
+        }
+    }
+    __syncwarp();     // the .sync.aligned tcgen05 instructions that follow need the warp converged
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t tc_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// Stage rows [row0, row0 + 128) of Zd as split TF32 tiles (canonical K-major layout, SBO = 512).
+__device__ __forceinline__ void tc_stage_z(const TcArgs &a, int64_t row0, unsigned char *hi_tile, unsigned char *lo_tile) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 1, k0 = (tid & 1) * 8;
+    const int64_t row = row0 + r;
+    const bool rv = row < a.n;
+    const float *src = a.Zd + row * a.ldz;
+#pragma unroll
+    for (int kg = 0; kg < 2; ++kg) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + kg * 4 + q;
+            const float x = (rv && k < a.d) ? __ldg(src + k) : 0.f;
+            h[q] = tc_tf32(x);
+            l[q] = tc_tf32(x - __uint_as_float(h[q]));
+        }
+        const int off = (r >> 3) * 512 + ((k0 >> 2) + kg) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+template <bool PROBE>
+__global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ double red[TC_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2;
+    const int I = PROBE ? a.probe_I : (int)blockIdx.x;
+    int j_begin, j_end;
+    if (PROBE) {
+        j_begin = a.probe_J;
+        j_end = a.probe_J + 1;
+    } else {
+        const int len = a.T - I, per = (len + a.splits - 1) / a.splits;
+        j_begin = I + (int)blockIdx.y * per;
+        j_end = min(a.T, j_begin + per);
+    }
+    const uint32_t bar_s = tc_smem_u32(smem + TC_OFF_BAR), bar_g = bar_s + 8;
+    const uint32_t zi_hi = tc_smem_u32(smem + TC_OFF_ZI_HI), zi_lo = tc_smem_u32(smem + TC_OFF_ZI_LO);
+    const uint32_t zj_hi = tc_smem_u32(smem + TC_OFF_ZJ_HI), zj_lo = tc_smem_u32(smem + TC_OFF_ZJ_LO);
+    const uint32_t sg_hi = tc_smem_u32(smem + TC_OFF_SG_HI), sg_lo = tc_smem_u32(smem + TC_OFF_SG_LO);
+
+    // ---- set-up: barriers, TMEM, the stationary row block ---------------------------------------------
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_g) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_stage_z(a, (int64_t)I * TC_TILE, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO);
+    if (j_begin < j_end) tc_stage_z(a, (int64_t)j_begin * TC_TILE, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
+    tc_fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+
+    constexpr uint32_t IDESC_S = tc_idesc(128, 128, 0, 0);    // A = Z_I K-major, B = Z_J K-major
+    constexpr uint32_t IDESC_GI = tc_idesc(128, 16, 0, 1);    // A = sigma K-major, B = Z_J MN-major
+    constexpr uint32_t IDESC_GJ = tc_idesc(128, 16, 1, 1);    // A = sigma MN-major (= sigma^T), B = Z_I MN-major
+
+    float gi[TC_D];
+#pragma unroll
+    for (int k = 0; k < TC_D; ++k) gi[k] = 0.f;
+    double lacc = 0.0;
+    const int64_t row = (int64_t)I * TC_TILE + 32 * q + lane;     // my query row (chain and G_I read-out)
+    const bool row_ok = row < a.n;
+    uint32_t phase = 0;
+
+    for (int J = j_begin; J < j_end; ++J) {
+        const bool diag = J == I;
+        // ---- S = Z_I Z_J^T, split precision: hi hi + lo hi + hi lo, two K = 8 steps each ------------------
+        if (tid == 0) {
+            const uint32_t A[3] = {zi_hi, zi_lo, zi_hi}, B[3] = {zj_hi, zj_hi, zj_lo};
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    tc_mma(tmem + TC_COL_S, tc_desc(A[t] + ks * 256, 128, 512), tc_desc(B[t] + ks * 256, 128, 512), IDESC_S,
+                           (t | ks) != 0);
+            tc_commit(bar_s);
+        }
+        tc_wait(bar_s, phase, a.err);
+        tc_fence_after();
+        // ---- element-wise chain: my row, 64 keys ----------------------------------------------------------
+        const int64_t key0 = (int64_t)J * TC_TILE + 64 * half;
+        const bool ragged = ((int64_t)I * TC_TILE + TC_TILE > a.n) || ((int64_t)J * TC_TILE + TC_TILE > a.n);
+        float msum = 0.f, prod = 1.f;
+        const int r = 32 * q + lane;
+        unsigned char *sg_h_row = smem + TC_OFF_SG_HI + (r >> 3) * 4096 + (r & 7) * 16;
+        unsigned char *sg_l_row = smem + TC_OFF_SG_LO + (r >> 3) * 4096 + (r & 7) * 16;
+#pragma unroll
+        for (int chunk = 0; chunk < 2; ++chunk) {
+            uint32_t v[32];
+            tc_ld32(tmem + lane_base + TC_COL_S + 64 * half + 32 * chunk, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                uint32_t hi4[4], lo4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 32 * chunk + 4 * g4 + e;            // column within my 64
+                    const float x = __uint_as_float(v[4 * g4 + e]);
+                    if (PROBE) a.probe_S[(int64_t)r * TC_TILE + 64 * half + c] = x;
+                    float ex, rc;
+                    const float t = -fabsf(x) * 1.4426950408889634f;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
+                    float one_e = 1.0f + ex;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
+                    float sg = (x >= 0.f) ? rc : ex * rc;
+                    if (ragged) {
+                        const bool ok = row_ok && (key0 + c < a.n);
+                        sg = ok ? sg : 0.f;
+                        one_e = ok ? one_e : 1.0f;
+                    }
+                    msum += fmaxf(x, 0.f);
+                    prod *= one_e;
+                    const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
+                    hi4[e] = hb;
+                    lo4[e] = __float_as_uint(sg - __uint_as_float(hb));
+                }
+                const int coff = (16 * half + 8 * chunk + g4) * 128;     // key group of 4 inside the tile
+                *reinterpret_cast<uint4 *>(sg_h_row + coff) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                *reinterpret_cast<uint4 *>(sg_l_row + coff) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            }
+        }
+        {
+            // sum softplus = sum max(x, 0) + ln prod (1 + e^-|x|): 64 factors in (1, 2] cannot overflow
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod));
+            const float tile_sum = msum + l2 * 0.6931471805599453f;
+            lacc += (double)(diag ? tile_sum : 2.f * tile_sum);
+        }
+        tc_fence_before();
+        tc_fence_async_smem();
+        __syncthreads();
+        // ---- gradients: G_I = sigma Z_J, G_J = sigma^T Z_I (sixteen K = 8 steps, three split terms) --------
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t SA[3] = {sg_hi, sg_lo, sg_hi};
+            const uint32_t ZB[3] = {zj_hi, zj_hi, zj_lo};
+            const uint32_t ZI[3] = {zi_hi, zi_hi, zi_lo};
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                for (int ks = 0; ks < 16; ++ks)
+                    tc_mma(tmem + TC_COL_GI, tc_desc(SA[t] + ks * 256, 128, 4096), tc_desc(ZB[t] + ks * 512, 512, 128),
+                           IDESC_GI, (t | ks) != 0);
+            if (!diag) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    for (int ks = 0; ks < 16; ++ks)
+                        tc_mma(tmem + TC_COL_GJ, tc_desc(SA[t] + ks * 4096, 4096, 128), tc_desc(ZI[t] + ks * 512, 512, 128),
+                               IDESC_GJ, (t | ks) != 0);
+            }
+            tc_commit(bar_g);
+        }
+        tc_wait(bar_g, phase, a.err);
+        tc_fence_after();
+        phase ^= 1u;
+        if (half == 0) {
+            uint32_t v[16];
+            tc_ld16(tmem + lane_base + TC_COL_GI, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int k = 0; k < TC_D; ++k) gi[k] += __uint_as_float(v[k]);
+            if (PROBE)
+                for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = __uint_as_float(v[k]);
+        } else if (!diag) {
+            uint32_t v[16];
+            tc_ld16(tmem + lane_base + TC_COL_GJ, v);
+            tc_wait_ld();
+            const int64_t key = (int64_t)J * TC_TILE + r;
+            if (PROBE) {
+                for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = __uint_as_float(v[k]);
+            } else if (key < a.n) {
+                float4 *o = reinterpret_cast<float4 *>(a.dzT_part + ((int64_t)I * a.n + key) * TC_D);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    o[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
+                                        __uint_as_float(v[4 * k4 + 3]));
+            }
+        }
+        // next key tile (both MMAs that read the old one have completed: bar_g)
+        if (J + 1 < j_end) tc_stage_z(a, (int64_t)(J + 1) * TC_TILE, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
+        tc_fence_before();
+        tc_fence_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    // ---- outputs of this CTA ---------------------------------------------------------------------------
+    if (!PROBE) {
+        if (half == 0 && row_ok) {
+            float4 *o = reinterpret_cast<float4 *>(a.dz_part + ((int64_t)blockIdx.y * a.n + row) * TC_D);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(gi[4 * k4], gi[4 * k4 + 1], gi[4 * k4 + 2], gi[4 * k4 + 3]);
+        }
+        double s = lacc;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < TC_THREADS / 32; ++w) t += red[w];
+            if (*reinterpret_cast<volatile uint32_t *>(a.err) != 0) t = __longlong_as_double(0x7ff8000000000000ll);   // a wait expired: NaN loss
+            a.loss_part[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+}
+
+// splits of the key range of a row block: enough CTAs for two waves, runs of at most ~16 tiles
+int dec_tc_splits(int64_t n) {
+    const int64_t T = cdiv(n, TC_TILE);
+    int64_t s = cdiv(T, 16);
+    const int64_t fill = cdiv(2 * 148, T);
+    if (fill > s) s = fill;
+    if (s > T) s = T;
+    if (s > 32) s = 32;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+cudaError_t dec_tc_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
+                          double *loss_part, uint32_t *err, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dec_dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(dec_dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    TcArgs a{};
+    a.Zd = Zd; a.ldz = ldz; a.n = n; a.d = d; a.T = (int)cdiv(n, TC_TILE); a.splits = splits;
+    a.dz_part = dz_part; a.dzT_part = dzT_part; a.loss_part = loss_part; a.err = err;
+    dim3 grid((unsigned)a.T, (unsigned)splits);
+    dec_dense_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace gae
+
+using namespace gae;
+
+extern "C" int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, int32_t tile_i, int32_t tile_j,
+                                          float *S, float *G_i, float *G_j, int32_t *timeouts, void *stream) {
+    GAE_CHECK_ARG(Zd && S && G_i && G_j && timeouts, "null pointer");
+    GAE_CHECK_ARG(n > 0 && d > 0 && d <= TC_D && ldz >= d, "needs 0 < d <= 16");
+    const int T = (int)cdiv(n, TC_TILE);
+    GAE_CHECK_ARG(tile_i >= 0 && tile_i <= tile_j && tile_j < T, "tile indices: 0 <= i <= j < ceil(n / 128)");
+    GAE_CUDA(cudaFuncSetAttribute(dec_dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *err = nullptr;
+    GAE_CUDA(cudaMalloc(&err, sizeof(uint32_t)));
+    GAE_CUDA(cudaMemsetAsync(err, 0, sizeof(uint32_t), st));
+    TcArgs a{};
+    a.Zd = Zd; a.ldz = ldz; a.n = n; a.d = d; a.T = T; a.splits = 1; a.err = err;
+    a.probe_S = S; a.probe_GI = G_i; a.probe_GJ = G_j; a.probe_I = tile_i; a.probe_J = tile_j;
+    dec_dense_tc_kernel<true><<<1, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    uint32_t h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, err, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(err);
+    if (e != cudaSuccess) {
+        set_error("gae_decoder_tile_probe_f32: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    count_launch();
+    *timeouts = (int32_t)h;
+    return GAE_OK;
+}

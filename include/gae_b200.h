@@ -242,6 +242,15 @@ int gae_batch_assemble(const int64_t *rowptr_all, const int32_t *col_all, const 
                        int64_t *out_rowptr, int32_t *out_col, const float *feat_all, int64_t ldf,
                        int32_t d, float *out_feat, int64_t ld_out, void *stream);
 
+/* Diagnostic of the tcgen05 / TMEM dense pass (csrc/decoder_tc.cu, the default for d <= 16 and n >= 512): runs
+ * ONE 128 x 128 tile (tile_i <= tile_j) through the kernel's own code path and returns what the tensor cores
+ * produced -- S = Z_I Z_J^T [128,128], G_i = sigmoid(S) Z_J [128,16], G_j = sigmoid(S)^T Z_I [128,16] (left
+ * untouched on a diagonal tile) -- so that each shared-memory / instruction descriptor can be checked against
+ * a host product on its own.  Synchronises the stream; *timeouts = bounded waits that expired (0 when sound). */
+int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, int32_t tile_i,
+                               int32_t tile_j, float *S, float *G_i, float *G_j, int32_t *timeouts,
+                               void *stream);
+
 /* ---- K7: halo exchange helpers (8e) -------------------------------------------------------- */
 /* Pack rows idx[0..m) of X into out (send buffer of the all-to-all-v). */
 int gae_gather_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t m, int32_t d,
