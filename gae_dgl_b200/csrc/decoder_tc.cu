@@ -4,31 +4,33 @@
 // Reference: logits = mm(zd, zd.t()) (gae.py:71) + BCEWithLogits and its backward
 // (train_inductive.py:44-51).  X = Zd Zd^T is symmetric whatever the graph is, so a tile (I, J), I < J,
 // is evaluated ONCE and feeds both row blocks:
-//     S      = Z_I Z_J^T                       128 x 128 logits        (tcgen05.mma, accumulator in TMEM)
+//     S      = Z_I Z_J^T                       128 x 128 logits        (tcgen05.mma SS, accumulator in TMEM)
 //     sigma  = sigmoid(S), loss += 2 softplus(S)                       (tcgen05.ld -> registers, MUFU chain)
-//     G_I   += sigma   Z_J    (rows of block I)                        (tcgen05.mma, sigma from shared memory)
-//     G_J    = sigma^T Z_I    (rows of block J, one partial per I)     (tcgen05.mma, the SAME sigma tile read
-//                                                                       M-major through its descriptor)
+//     G_I   += sigma   Z_J    (rows of block I)                        (tcgen05.mma TS: sigma is the TMEM A operand)
+//     G_J    = sigma^T Z_I    (rows of block J, one partial per I)     (tcgen05.mma SS: sigma^T from shared memory)
 // Diagonal tiles contribute once and skip G_J.  That halves the S GEMM and -- the actual bound for d = 16 --
 // the ex2 + rcp chain: 2 MUFU ops per pair at 16 per clock per SM.
 //
-// Precision: operands are split hi + lo (hi = TF32 rounding, lo = remainder) and every product is
-// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (~2^-21 relative), the scheme of the mma.sync kernel
-// this replaces, under the same 1e-5 parity tests.  Gradient accumulators leave TMEM after every tile and
-// are summed in fp32 registers (tensor-core accumulation truncates; chains stay 128 keys long).
+// Precision: operands are split hi + lo (hi = TF32, lo = remainder) and every product is hi*hi + lo*hi + hi*lo
+// with fp32 accumulation in TMEM (~2^-21 relative), the scheme of the mma.sync kernel this replaces, under the
+// same 1e-5 parity tests.  For the gradient products the two terms that share sigma_hi run as ONE MMA against
+// [Z_hi | Z_lo] (N = 32, the halves are added at read-out).  Gradient accumulators leave TMEM after every tile
+// and are summed in fp32 registers (tensor-core accumulation truncates; chains stay 128 keys long).
 //
-// Shared-memory operand layout: the no-swizzle canonical form, 8 x 16-byte core matrices.  A tile stored as
-//     off(r, c) = (r / 8) * SBO + (c / 4) * 128 + (r % 8) * 16 + (c % 4) * 4
-// is K-major for a product contracting over c (LBO = 128, SBO) and MN-major for one contracting over r
-// (SBO' = 128, LBO' = SBO): Z tiles (SBO = 512) serve as A/B of S and as B of both gradient products,
-// the sigma tile (SBO = 4096) as A of G_I (K-major) and as A of G_J (MN-major) -- no transposed copies.
+// Shared-memory operands: all K-major in the no-swizzle canonical form (8-row x 16-byte core matrices),
+//     off(m, k) = (m / 8) * SBO + (k / 4) * LBO + (m % 8) * 16 + (k % 4) * 4
+// (TF32 operands may be MN-major only in the 128B/32B-atom swizzle; measured here: the plain MN-major form
+// yields zeros).  So the kernel keeps, per 128-row block of Zd, a [row][dim] tile for S and a [dim][row] tile for
+// the gradient products, and writes sigma twice: to TMEM (lane = query row, column = key: the A operand of
+// sigma Z_J) and transposed to shared memory ([key][row], LBO = 144 so that the 32 lanes of a warp, which hold
+// 32 consecutive rows of one key column, hit 32 different banks).
 //
-// One CTA (256 threads, 1 per SM: 160 KB of shared memory) walks a run of tiles J of one row block I.
-// Thread 0 issues every MMA; completion comes back through tcgen05.commit on an mbarrier; all eight warps
-// run the element-wise chain (warp w: TMEM lanes 32 (w % 4).., columns 64 (w / 4)..).  Deterministic: the
-// G_I partial of CTA (I, s) and the G_J partial of tile (I, J) have their own slots, summed in fixed order by
-// dec_finalize_kernel.  Spin loops are bounded (%globaltimer): on expiry an error word is set and the kernel
-// falls through, so a protocol fault yields a reported error, never a hung GPU.
+// One CTA (256 threads, 1 per SM: 208 KB of shared memory, all 512 TMEM columns) walks a run of tiles J of one
+// row block I.  Thread 0 issues every MMA; completion comes back through tcgen05.commit on an mbarrier; all
+// eight warps run the element-wise chain (warp w: TMEM lanes 32 (w % 4).., columns 64 (w / 4)..).
+// Deterministic: the G_I partial of CTA (I, s) and the G_J partial of tile (I, J) have their own slots, summed
+// in fixed order by dec_finalize_kernel.  Waits are bounded (%globaltimer): on expiry an error word is set, the
+// loss becomes NaN and the kernel falls through -- a protocol fault is reported, never a hung GPU.
 #include "common.cuh"
 
 namespace gae {
@@ -36,14 +38,19 @@ namespace gae {
 constexpr int TC_THREADS = 256;
 constexpr int TC_TILE = 128;
 constexpr int TC_D = 16;
-constexpr uint32_t TC_TMEM_COLS = 256;   // S: 128 | G_I: 16 | G_J: 16 (power of two >= 160)
-constexpr uint32_t TC_COL_S = 0, TC_COL_GI = 128, TC_COL_GJ = 144;
-constexpr int TC_Z_BYTES = TC_TILE * TC_D * 4;        // 8 KB
-constexpr int TC_SG_BYTES = TC_TILE * TC_TILE * 4;    // 64 KB
+constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr uint32_t TC_COL_S = 0, TC_COL_SGH = 128, TC_COL_SGL = 256, TC_COL_GI = 384, TC_COL_GJ = 416;
+// shared memory map (bytes)
+constexpr int TC_Z_BYTES = TC_TILE * TC_D * 4;             // [row][dim] tile, K = dim: LBO 128, SBO 512
+constexpr int TC_ZT_BYTES = 2 * TC_D * TC_TILE * 4;        // [hi dims | lo dims][row] tile, K = row: LBO 128, SBO 4096
+constexpr int TC_SGT_LBO = 144, TC_SGT_SBO = 32 * TC_SGT_LBO;   // sigma^T [key][row] tile, K = row
+constexpr int TC_SGT_BYTES = 16 * TC_SGT_SBO;              // 73 728
 constexpr int TC_OFF_ZI_HI = 0, TC_OFF_ZI_LO = TC_Z_BYTES, TC_OFF_ZJ_HI = 2 * TC_Z_BYTES, TC_OFF_ZJ_LO = 3 * TC_Z_BYTES;
-constexpr int TC_OFF_SG_HI = 4 * TC_Z_BYTES, TC_OFF_SG_LO = TC_OFF_SG_HI + TC_SG_BYTES;
-constexpr int TC_OFF_BAR = TC_OFF_SG_LO + TC_SG_BYTES;
+constexpr int TC_OFF_ZIT = 4 * TC_Z_BYTES, TC_OFF_ZJT = TC_OFF_ZIT + TC_ZT_BYTES;
+constexpr int TC_OFF_SGT_HI = TC_OFF_ZJT + TC_ZT_BYTES, TC_OFF_SGT_LO = TC_OFF_SGT_HI + TC_SGT_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_SGT_LO + TC_SGT_BYTES;
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 64;
+static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct TcArgs {
     const float *Zd;
@@ -61,21 +68,28 @@ struct TcArgs {
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), LBO >> 4 at
-// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64))
+// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64)).  Advancing the start address by
+// b bytes is desc + (b >> 4).
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
-// instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -111,6 +125,9 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t 
     }
     __syncwarp();     // the .sync.aligned tcgen05 instructions that follow need the warp converged
 }
+#define TC_R32(v) \
+    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17], v[18], \
+        v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -123,16 +140,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t tc_tf32(float x) {
     uint32_t r;
@@ -140,26 +160,39 @@ __device__ __forceinline__ uint32_t tc_tf32(float x) {
     return r;
 }
 
-// Stage rows [row0, row0 + 128) of Zd as split TF32 tiles (canonical K-major layout, SBO = 512).
-__device__ __forceinline__ void tc_stage_z(const TcArgs &a, int64_t row0, unsigned char *hi_tile, unsigned char *lo_tile) {
+// Thread t of the CTA handles row t / 2, dims 8 (t % 2) .. + 8 of a 128-row block of Zd.
+__device__ __forceinline__ void tc_load_z(const TcArgs &a, int64_t row0, float (&x)[8]) {
     const int tid = threadIdx.x;
-    const int r = tid >> 1, k0 = (tid & 1) * 8;
-    const int64_t row = row0 + r;
+    const int64_t row = row0 + (tid >> 1);
+    const int k0 = (tid & 1) * 8;
     const bool rv = row < a.n;
     const float *src = a.Zd + row * a.ldz;
 #pragma unroll
-    for (int kg = 0; kg < 2; ++kg) {
-        uint32_t h[4], l[4];
+    for (int k = 0; k < 8; ++k) x[k] = (rv && k0 + k < a.d) ? __ldg(src + k0 + k) : 0.f;
+}
+// ... and stores it split into TF32 hi / lo in both layouts: [row][dim] (hi tile, lo tile) and [hi | lo dims][row].
+__device__ __forceinline__ void tc_store_z(const float (&x)[8], unsigned char *hi_tile, unsigned char *lo_tile, unsigned char *t_tile) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 1, k0 = (tid & 1) * 8;
+    uint32_t h[8], l[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = k0 + kg * 4 + q;
-            const float x = (rv && k < a.d) ? __ldg(src + k) : 0.f;
-            h[q] = tc_tf32(x);
-            l[q] = tc_tf32(x - __uint_as_float(h[q]));
-        }
+    for (int k = 0; k < 8; ++k) {
+        h[k] = tc_tf32(x[k]);
+        l[k] = tc_tf32(x[k] - __uint_as_float(h[k]));
+    }
+#pragma unroll
+    for (int kg = 0; kg < 2; ++kg) {
         const int off = (r >> 3) * 512 + ((k0 >> 2) + kg) * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[4 * kg], h[4 * kg + 1], h[4 * kg + 2], h[4 * kg + 3]);
+        *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[4 * kg], l[4 * kg + 1], l[4 * kg + 2], l[4 * kg + 3]);
+    }
+    // transposed: "row" index n = dim (hi) or 16 + dim (lo), K index = r
+    const int toff = (r >> 2) * 128 + (r & 3) * 4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int dim = k0 + k;
+        *reinterpret_cast<uint32_t *>(t_tile + (dim >> 3) * 4096 + (dim & 7) * 16 + toff) = h[k];
+        *reinterpret_cast<uint32_t *>(t_tile + ((16 + dim) >> 3) * 4096 + (dim & 7) * 16 + toff) = l[k];
     }
 }
 
@@ -181,9 +214,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         j_end = min(a.T, j_begin + per);
     }
     const uint32_t bar_s = tc_smem_u32(smem + TC_OFF_BAR), bar_g = bar_s + 8;
-    const uint32_t zi_hi = tc_smem_u32(smem + TC_OFF_ZI_HI), zi_lo = tc_smem_u32(smem + TC_OFF_ZI_LO);
-    const uint32_t zj_hi = tc_smem_u32(smem + TC_OFF_ZJ_HI), zj_lo = tc_smem_u32(smem + TC_OFF_ZJ_LO);
-    const uint32_t sg_hi = tc_smem_u32(smem + TC_OFF_SG_HI), sg_lo = tc_smem_u32(smem + TC_OFF_SG_LO);
 
     // ---- set-up: barriers, TMEM, the stationary row block ---------------------------------------------
     if (tid == 0) {
@@ -198,8 +228,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    tc_stage_z(a, (int64_t)I * TC_TILE, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO);
-    if (j_begin < j_end) tc_stage_z(a, (int64_t)j_begin * TC_TILE, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
+    {
+        float x[8];
+        tc_load_z(a, (int64_t)I * TC_TILE, x);
+        tc_store_z(x, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO, smem + TC_OFF_ZIT);
+        if (j_begin < j_end) {
+            tc_load_z(a, (int64_t)j_begin * TC_TILE, x);
+            tc_store_z(x, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO, smem + TC_OFF_ZJT);
+        }
+    }
     tc_fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -207,75 +244,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
 
-    constexpr uint32_t IDESC_S = tc_idesc(128, 128, 0, 0);    // A = Z_I K-major, B = Z_J K-major
-    constexpr uint32_t IDESC_GI = tc_idesc(128, 16, 0, 1);    // A = sigma K-major, B = Z_J MN-major
-    constexpr uint32_t IDESC_GJ = tc_idesc(128, 16, 1, 1);    // A = sigma MN-major (= sigma^T), B = Z_I MN-major
+    constexpr uint32_t IDESC_S = tc_idesc(128, 128);
+    constexpr uint32_t IDESC_G32 = tc_idesc(128, 32);     // A x [Z_hi | Z_lo]
+    constexpr uint32_t IDESC_G16 = tc_idesc(128, 16);     // A x Z_hi
+    // descriptors at K step 0 (thread 0 issues; the others never use them)
+    const uint64_t d_zi_hi = tc_desc(tc_smem_u32(smem + TC_OFF_ZI_HI), 128, 512), d_zi_lo = tc_desc(tc_smem_u32(smem + TC_OFF_ZI_LO), 128, 512);
+    const uint64_t d_zj_hi = tc_desc(tc_smem_u32(smem + TC_OFF_ZJ_HI), 128, 512), d_zj_lo = tc_desc(tc_smem_u32(smem + TC_OFF_ZJ_LO), 128, 512);
+    const uint64_t d_zit = tc_desc(tc_smem_u32(smem + TC_OFF_ZIT), 128, 4096), d_zjt = tc_desc(tc_smem_u32(smem + TC_OFF_ZJT), 128, 4096);
+    const uint64_t d_sgt_hi = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_HI), TC_SGT_LBO, TC_SGT_SBO);
+    const uint64_t d_sgt_lo = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_LO), TC_SGT_LBO, TC_SGT_SBO);
 
     float gi[TC_D];
 #pragma unroll
     for (int k = 0; k < TC_D; ++k) gi[k] = 0.f;
     double lacc = 0.0;
-    const int64_t row = (int64_t)I * TC_TILE + 32 * q + lane;     // my query row (chain and G_I read-out)
+    const int r = 32 * q + lane;                                  // my row inside the tile
+    const int64_t row = (int64_t)I * TC_TILE + r;                 // my query row (chain and G_I read-out)
     const bool row_ok = row < a.n;
+    // where my row of sigma^T goes: K index = r, for key c add (c / 8) * SBO + (c % 8) * 16
+    const int sgt_row_off = (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
     uint32_t phase = 0;
 
     for (int J = j_begin; J < j_end; ++J) {
         const bool diag = J == I;
         // ---- S = Z_I Z_J^T, split precision: hi hi + lo hi + hi lo, two K = 8 steps each ------------------
         if (tid == 0) {
-            const uint32_t A[3] = {zi_hi, zi_lo, zi_hi}, B[3] = {zj_hi, zj_hi, zj_lo};
 #pragma unroll
-            for (int t = 0; t < 3; ++t)
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    tc_mma(tmem + TC_COL_S, tc_desc(A[t] + ks * 256, 128, 512), tc_desc(B[t] + ks * 256, 128, 512), IDESC_S,
-                           (t | ks) != 0);
+            for (int ks = 0; ks < 2; ++ks) {
+                tc_mma_ss(tmem + TC_COL_S, d_zi_hi + ks * 16, d_zj_hi + ks * 16, IDESC_S, ks != 0);
+                tc_mma_ss(tmem + TC_COL_S, d_zi_lo + ks * 16, d_zj_hi + ks * 16, IDESC_S, 1);
+                tc_mma_ss(tmem + TC_COL_S, d_zi_hi + ks * 16, d_zj_lo + ks * 16, IDESC_S, 1);
+            }
             tc_commit(bar_s);
         }
+        // the next key tile's rows travel from HBM / L2 while this tile is processed
+        float xn[8];
+        const bool more = J + 1 < j_end;
+        if (more) tc_load_z(a, (int64_t)(J + 1) * TC_TILE, xn);
         tc_wait(bar_s, phase, a.err);
         tc_fence_after();
         // ---- element-wise chain: my row, 64 keys ----------------------------------------------------------
         const int64_t key0 = (int64_t)J * TC_TILE + 64 * half;
         const bool ragged = ((int64_t)I * TC_TILE + TC_TILE > a.n) || ((int64_t)J * TC_TILE + TC_TILE > a.n);
         float msum = 0.f, prod = 1.f;
-        const int r = 32 * q + lane;
-        unsigned char *sg_h_row = smem + TC_OFF_SG_HI + (r >> 3) * 4096 + (r & 7) * 16;
-        unsigned char *sg_l_row = smem + TC_OFF_SG_LO + (r >> 3) * 4096 + (r & 7) * 16;
 #pragma unroll
         for (int chunk = 0; chunk < 2; ++chunk) {
-            uint32_t v[32];
-            tc_ld32(tmem + lane_base + TC_COL_S + 64 * half + 32 * chunk, v);
+            uint32_t v[32], lo[32];
+            const int c0 = 64 * half + 32 * chunk;                     // first key of this chunk inside the tile
+            tc_ld32(tmem + lane_base + TC_COL_S + c0, v);
             tc_wait_ld();
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                uint32_t hi4[4], lo4[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 32 * chunk + 4 * g4 + e;            // column within my 64
-                    const float x = __uint_as_float(v[4 * g4 + e]);
-                    if (PROBE) a.probe_S[(int64_t)r * TC_TILE + 64 * half + c] = x;
-                    float ex, rc;
-                    const float t = -fabsf(x) * 1.4426950408889634f;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
-                    float one_e = 1.0f + ex;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
-                    float sg = (x >= 0.f) ? rc : ex * rc;
-                    if (ragged) {
-                        const bool ok = row_ok && (key0 + c < a.n);
-                        sg = ok ? sg : 0.f;
-                        one_e = ok ? one_e : 1.0f;
-                    }
-                    msum += fmaxf(x, 0.f);
-                    prod *= one_e;
-                    const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
-                    hi4[e] = hb;
-                    lo4[e] = __float_as_uint(sg - __uint_as_float(hb));
+            for (int e = 0; e < 32; ++e) {
+                const float x = __uint_as_float(v[e]);
+                if (PROBE) a.probe_S[(int64_t)r * TC_TILE + c0 + e] = x;
+                float ex, rc;
+                const float t = -fabsf(x) * 1.4426950408889634f;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
+                float one_e = 1.0f + ex;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
+                float sg = (x >= 0.f) ? rc : ex * rc;
+                if (ragged) {
+                    const bool ok = row_ok && (key0 + 32 * chunk + e < a.n);
+                    sg = ok ? sg : 0.f;
+                    one_e = ok ? one_e : 1.0f;
                 }
-                const int coff = (16 * half + 8 * chunk + g4) * 128;     // key group of 4 inside the tile
-                *reinterpret_cast<uint4 *>(sg_h_row + coff) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-                *reinterpret_cast<uint4 *>(sg_l_row + coff) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                msum += fmaxf(x, 0.f);
+                prod *= one_e;
+                const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
+                v[e] = hb;                                             // sigma hi replaces the logit
+                lo[e] = __float_as_uint(sg - __uint_as_float(hb));
+                const int c = c0 + e;
+                const int off = (c >> 3) * TC_SGT_SBO + (c & 7) * 16 + sgt_row_off;
+                *reinterpret_cast<uint32_t *>(smem + TC_OFF_SGT_HI + off) = hb;
+                *reinterpret_cast<uint32_t *>(smem + TC_OFF_SGT_LO + off) = lo[e];
             }
+            tc_st32(tmem + lane_base + TC_COL_SGH + c0, v);
+            tc_st32(tmem + lane_base + TC_COL_SGL + c0, lo);
         }
+        tc_wait_st();
         {
             // sum softplus = sum max(x, 0) + ln prod (1 + e^-|x|): 64 factors in (1, 2] cannot overflow
             float l2;
@@ -286,23 +332,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         tc_fence_before();
         tc_fence_async_smem();
         __syncthreads();
-        // ---- gradients: G_I = sigma Z_J, G_J = sigma^T Z_I (sixteen K = 8 steps, three split terms) --------
+        // ---- gradients, sixteen K = 8 steps: sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi ----------------------------
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t SA[3] = {sg_hi, sg_lo, sg_hi};
-            const uint32_t ZB[3] = {zj_hi, zj_hi, zj_lo};
-            const uint32_t ZI[3] = {zi_hi, zi_hi, zi_lo};
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-                for (int ks = 0; ks < 16; ++ks)
-                    tc_mma(tmem + TC_COL_GI, tc_desc(SA[t] + ks * 256, 128, 4096), tc_desc(ZB[t] + ks * 512, 512, 128),
-                           IDESC_GI, (t | ks) != 0);
+            for (int ks = 0; ks < 16; ++ks) {      // G_I = sigma Z_J: A = sigma in TMEM (8 columns per step), B = Z_J^T tile
+                tc_mma_ts(tmem + TC_COL_GI, tmem + TC_COL_SGH + 8 * ks, d_zjt + ks * 16, IDESC_G32, ks != 0);
+                tc_mma_ts(tmem + TC_COL_GI, tmem + TC_COL_SGL + 8 * ks, d_zjt + ks * 16, IDESC_G16, 1);
+            }
             if (!diag) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t)
-                    for (int ks = 0; ks < 16; ++ks)
-                        tc_mma(tmem + TC_COL_GJ, tc_desc(SA[t] + ks * 4096, 4096, 128), tc_desc(ZI[t] + ks * 512, 512, 128),
-                               IDESC_GJ, (t | ks) != 0);
+                for (int ks = 0; ks < 16; ++ks) {  // G_J = sigma^T Z_I: A = sigma^T tile (two 4-row groups per step), B = Z_I^T tile
+                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_hi + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G32, ks != 0);
+                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_lo + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G16, 1);
+                }
             }
             tc_commit(bar_g);
         }
@@ -310,30 +351,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         tc_fence_after();
         phase ^= 1u;
         if (half == 0) {
-            uint32_t v[16];
-            tc_ld16(tmem + lane_base + TC_COL_GI, v);
+            uint32_t v[32];
+            tc_ld32(tmem + lane_base + TC_COL_GI, v);
             tc_wait_ld();
 #pragma unroll
-            for (int k = 0; k < TC_D; ++k) gi[k] += __uint_as_float(v[k]);
+            for (int k = 0; k < TC_D; ++k) gi[k] += __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
             if (PROBE)
-                for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = __uint_as_float(v[k]);
+                for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
         } else if (!diag) {
-            uint32_t v[16];
-            tc_ld16(tmem + lane_base + TC_COL_GJ, v);
+            uint32_t v[32];
+            tc_ld32(tmem + lane_base + TC_COL_GJ, v);
             tc_wait_ld();
             const int64_t key = (int64_t)J * TC_TILE + r;
             if (PROBE) {
-                for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = __uint_as_float(v[k]);
+                for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
             } else if (key < a.n) {
                 float4 *o = reinterpret_cast<float4 *>(a.dzT_part + ((int64_t)I * a.n + key) * TC_D);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                    o[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]),
-                                        __uint_as_float(v[4 * k4 + 3]));
+                    o[k4] = make_float4(__uint_as_float(v[4 * k4]) + __uint_as_float(v[16 + 4 * k4]),
+                                        __uint_as_float(v[4 * k4 + 1]) + __uint_as_float(v[17 + 4 * k4]),
+                                        __uint_as_float(v[4 * k4 + 2]) + __uint_as_float(v[18 + 4 * k4]),
+                                        __uint_as_float(v[4 * k4 + 3]) + __uint_as_float(v[19 + 4 * k4]));
             }
         }
-        // next key tile (both MMAs that read the old one have completed: bar_g)
-        if (J + 1 < j_end) tc_stage_z(a, (int64_t)(J + 1) * TC_TILE, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
+        // next key tile (every MMA that read the old one has completed: bar_g)
+        if (more) tc_store_z(xn, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO, smem + TC_OFF_ZJT);
         tc_fence_before();
         tc_fence_async_smem();
         __syncthreads();
