@@ -35,11 +35,11 @@
 
 namespace gae {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;
 constexpr int TC_TILE = 128;
 constexpr int TC_D = 16;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr uint32_t TC_COL_S = 0, TC_COL_SGH = 128, TC_COL_SGL = 256, TC_COL_GI = 384, TC_COL_GJ = 416;
+constexpr uint32_t TC_COL_S0 = 0, TC_COL_S1 = 128, TC_COL_SGL = 256, TC_COL_GI = 384, TC_COL_GJ = 416;   // sigma_hi overwrites S in place
 // shared memory map (bytes)
 constexpr int TC_Z_BYTES = TC_TILE * TC_D * 4;             // [row][dim] tile, K = dim: LBO 128, SBO 512
 constexpr int TC_ZT_BYTES = 2 * TC_D * TC_TILE * 4;        // [hi dims | lo dims][row] tile, K = row: LBO 128, SBO 4096
@@ -160,39 +160,42 @@ __device__ __forceinline__ uint32_t tc_tf32(float x) {
     return r;
 }
 
-// Thread t of the CTA handles row t / 2, dims 8 (t % 2) .. + 8 of a 128-row block of Zd.
-__device__ __forceinline__ void tc_load_z(const TcArgs &a, int64_t row0, float (&x)[8]) {
+// Thread t of the CTA handles row t / 4, dims 4 (t % 4) .. + 4 of a 128-row block of Zd.
+__device__ __forceinline__ void tc_load_z(const TcArgs &a, int64_t row0, float (&x)[4]) {
     const int tid = threadIdx.x;
-    const int64_t row = row0 + (tid >> 1);
-    const int k0 = (tid & 1) * 8;
+    const int64_t row = row0 + (tid >> 2);
+    const int k0 = (tid & 3) * 4;
     const bool rv = row < a.n;
     const float *src = a.Zd + row * a.ldz;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (rv && k0 + k < a.d) ? __ldg(src + k0 + k) : 0.f;
+    for (int k = 0; k < 4; ++k) x[k] = (rv && k0 + k < a.d) ? __ldg(src + k0 + k) : 0.f;
 }
-// ... and stores it split into TF32 hi / lo in both layouts: [row][dim] (hi tile, lo tile) and [hi | lo dims][row].
-__device__ __forceinline__ void tc_store_z(const float (&x)[8], unsigned char *hi_tile, unsigned char *lo_tile, unsigned char *t_tile) {
+// [row][dim] tiles (K = dim): hi and lo, LBO 128 / SBO 512
+__device__ __forceinline__ void tc_store_z(const float (&x)[4], unsigned char *hi_tile, unsigned char *lo_tile) {
     const int tid = threadIdx.x;
-    const int r = tid >> 1, k0 = (tid & 1) * 8;
-    uint32_t h[8], l[8];
+    const int r = tid >> 2, g = tid & 3;
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
         h[k] = tc_tf32(x[k]);
         l[k] = tc_tf32(x[k] - __uint_as_float(h[k]));
     }
-#pragma unroll
-    for (int kg = 0; kg < 2; ++kg) {
-        const int off = (r >> 3) * 512 + ((k0 >> 2) + kg) * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[4 * kg], h[4 * kg + 1], h[4 * kg + 2], h[4 * kg + 3]);
-        *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[4 * kg], l[4 * kg + 1], l[4 * kg + 2], l[4 * kg + 3]);
-    }
-    // transposed: "row" index n = dim (hi) or 16 + dim (lo), K index = r
+    const int off = (r >> 3) * 512 + g * 128 + (r & 7) * 16;
+    *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// [hi dims | lo dims][row] tile (K = row): "row" index n = dim (hi) or 16 + dim (lo), LBO 128 / SBO 4096
+__device__ __forceinline__ void tc_store_zt(const float (&x)[4], unsigned char *t_tile) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, g = tid & 3;
     const int toff = (r >> 2) * 128 + (r & 3) * 4;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int dim = k0 + k;
-        *reinterpret_cast<uint32_t *>(t_tile + (dim >> 3) * 4096 + (dim & 7) * 16 + toff) = h[k];
-        *reinterpret_cast<uint32_t *>(t_tile + ((16 + dim) >> 3) * 4096 + (dim & 7) * 16 + toff) = l[k];
+    for (int k = 0; k < 4; ++k) {
+        const int dim = 4 * g + k;
+        const uint32_t h = tc_tf32(x[k]);
+        const uint32_t l = tc_tf32(x[k] - __uint_as_float(h));
+        *reinterpret_cast<uint32_t *>(t_tile + (dim >> 3) * 4096 + (dim & 7) * 16 + toff) = h;
+        *reinterpret_cast<uint32_t *>(t_tile + (2 + (dim >> 3)) * 4096 + (dim & 7) * 16 + toff) = l;
     }
 }
 
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     __shared__ uint32_t tmem_slot;
     __shared__ double red[TC_THREADS / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter, key quarter of the tile
     const int I = PROBE ? a.probe_I : (int)blockIdx.x;
     int j_begin, j_end;
     if (PROBE) {
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     }
     const uint32_t bar_s = tc_smem_u32(smem + TC_OFF_BAR), bar_g = bar_s + 8;
 
-    // ---- set-up: barriers, TMEM, the stationary row block ---------------------------------------------
+    // ---- set-up: barriers, TMEM, the stationary row block, the first key block ---------------------------
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_g) : "memory");
@@ -228,13 +231,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    float xcur[4] = {0.f, 0.f, 0.f, 0.f};               // my 4 values of the key block in flight
     {
-        float x[8];
+        float x[4];
         tc_load_z(a, (int64_t)I * TC_TILE, x);
-        tc_store_z(x, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO, smem + TC_OFF_ZIT);
+        tc_store_z(x, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO);
+        tc_store_zt(x, smem + TC_OFF_ZIT);
         if (j_begin < j_end) {
-            tc_load_z(a, (int64_t)j_begin * TC_TILE, x);
-            tc_store_z(x, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO, smem + TC_OFF_ZJT);
+            tc_load_z(a, (int64_t)j_begin * TC_TILE, xcur);
+            tc_store_z(xcur, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
         }
     }
     tc_fence_async_smem();
@@ -254,6 +259,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     const uint64_t d_sgt_hi = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_HI), TC_SGT_LBO, TC_SGT_SBO);
     const uint64_t d_sgt_lo = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_LO), TC_SGT_LBO, TC_SGT_SBO);
 
+    // S = Z_I Z_J^T into S buffer `buf`, split precision: hi hi + lo hi + hi lo, two K = 8 steps each
+    auto issue_s = [&](int buf) {
+        const uint32_t d = tmem + (buf ? TC_COL_S1 : TC_COL_S0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            tc_mma_ss(d, d_zi_hi + ks * 16, d_zj_hi + ks * 16, IDESC_S, ks != 0);
+            tc_mma_ss(d, d_zi_lo + ks * 16, d_zj_hi + ks * 16, IDESC_S, 1);
+            tc_mma_ss(d, d_zi_hi + ks * 16, d_zj_lo + ks * 16, IDESC_S, 1);
+        }
+        tc_commit(bar_s);
+    };
+    if (tid == 0 && j_begin < j_end) issue_s(0);
+
     float gi[TC_D];
 #pragma unroll
     for (int k = 0; k < TC_D; ++k) gi[k] = 0.f;
@@ -261,96 +279,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     const int r = 32 * q + lane;                                  // my row inside the tile
     const int64_t row = (int64_t)I * TC_TILE + r;                 // my query row (chain and G_I read-out)
     const bool row_ok = row < a.n;
-    // where my row of sigma^T goes: K index = r, for key c add (c / 8) * SBO + (c % 8) * 16
-    const int sgt_row_off = (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
-    uint32_t phase = 0;
+    // where my row of sigma^T goes: K index = r; key c adds (c / 8) * SBO + (c % 8) * 16
+    unsigned char *sgt_hi_row = smem + TC_OFF_SGT_HI + (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
+    unsigned char *sgt_lo_row = smem + TC_OFF_SGT_LO + (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
 
-    for (int J = j_begin; J < j_end; ++J) {
-        const bool diag = J == I;
-        // ---- S = Z_I Z_J^T, split precision: hi hi + lo hi + hi lo, two K = 8 steps each ------------------
-        if (tid == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                tc_mma_ss(tmem + TC_COL_S, d_zi_hi + ks * 16, d_zj_hi + ks * 16, IDESC_S, ks != 0);
-                tc_mma_ss(tmem + TC_COL_S, d_zi_lo + ks * 16, d_zj_hi + ks * 16, IDESC_S, 1);
-                tc_mma_ss(tmem + TC_COL_S, d_zi_hi + ks * 16, d_zj_lo + ks * 16, IDESC_S, 1);
-            }
-            tc_commit(bar_s);
-        }
-        // the next key tile's rows travel from HBM / L2 while this tile is processed
-        float xn[8];
-        const bool more = J + 1 < j_end;
-        if (more) tc_load_z(a, (int64_t)(J + 1) * TC_TILE, xn);
-        tc_wait(bar_s, phase, a.err);
-        tc_fence_after();
-        // ---- element-wise chain: my row, 64 keys ----------------------------------------------------------
-        const int64_t key0 = (int64_t)J * TC_TILE + 64 * half;
-        const bool ragged = ((int64_t)I * TC_TILE + TC_TILE > a.n) || ((int64_t)J * TC_TILE + TC_TILE > a.n);
-        float msum = 0.f, prod = 1.f;
-#pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
-            uint32_t v[32], lo[32];
-            const int c0 = 64 * half + 32 * chunk;                     // first key of this chunk inside the tile
-            tc_ld32(tmem + lane_base + TC_COL_S + c0, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float x = __uint_as_float(v[e]);
-                if (PROBE) a.probe_S[(int64_t)r * TC_TILE + c0 + e] = x;
-                float ex, rc;
-                const float t = -fabsf(x) * 1.4426950408889634f;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
-                float one_e = 1.0f + ex;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
-                float sg = (x >= 0.f) ? rc : ex * rc;
-                if (ragged) {
-                    const bool ok = row_ok && (key0 + 32 * chunk + e < a.n);
-                    sg = ok ? sg : 0.f;
-                    one_e = ok ? one_e : 1.0f;
-                }
-                msum += fmaxf(x, 0.f);
-                prod *= one_e;
-                const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
-                v[e] = hb;                                             // sigma hi replaces the logit
-                lo[e] = __float_as_uint(sg - __uint_as_float(hb));
-                const int c = c0 + e;
-                const int off = (c >> 3) * TC_SGT_SBO + (c & 7) * 16 + sgt_row_off;
-                *reinterpret_cast<uint32_t *>(smem + TC_OFF_SGT_HI + off) = hb;
-                *reinterpret_cast<uint32_t *>(smem + TC_OFF_SGT_LO + off) = lo[e];
-            }
-            tc_st32(tmem + lane_base + TC_COL_SGH + c0, v);
-            tc_st32(tmem + lane_base + TC_COL_SGL + c0, lo);
-        }
-        tc_wait_st();
-        {
-            // sum softplus = sum max(x, 0) + ln prod (1 + e^-|x|): 64 factors in (1, 2] cannot overflow
-            float l2;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod));
-            const float tile_sum = msum + l2 * 0.6931471805599453f;
-            lacc += (double)(diag ? tile_sum : 2.f * tile_sum);
-        }
-        tc_fence_before();
-        tc_fence_async_smem();
-        __syncthreads();
-        // ---- gradients, sixteen K = 8 steps: sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi ----------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < 16; ++ks) {      // G_I = sigma Z_J: A = sigma in TMEM (8 columns per step), B = Z_J^T tile
-                tc_mma_ts(tmem + TC_COL_GI, tmem + TC_COL_SGH + 8 * ks, d_zjt + ks * 16, IDESC_G32, ks != 0);
-                tc_mma_ts(tmem + TC_COL_GI, tmem + TC_COL_SGL + 8 * ks, d_zjt + ks * 16, IDESC_G16, 1);
-            }
-            if (!diag) {
-                for (int ks = 0; ks < 16; ++ks) {  // G_J = sigma^T Z_I: A = sigma^T tile (two 4-row groups per step), B = Z_I^T tile
-                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_hi + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G32, ks != 0);
-                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_lo + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G16, 1);
-                }
-            }
-            tc_commit(bar_g);
-        }
-        tc_wait(bar_g, phase, a.err);
-        tc_fence_after();
-        phase ^= 1u;
-        if (half == 0) {
+    // gradient tiles of key block Jr leave TMEM: G_I into my registers (key quarter 0), G_J into its slot (quarter 1)
+    auto read_out = [&](int Jr) {
+        if (cq == 0) {
             uint32_t v[32];
             tc_ld32(tmem + lane_base + TC_COL_GI, v);
             tc_wait_ld();
@@ -358,11 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
             for (int k = 0; k < TC_D; ++k) gi[k] += __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
             if (PROBE)
                 for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
-        } else if (!diag) {
+        } else if (cq == 1 && Jr != I) {
             uint32_t v[32];
             tc_ld32(tmem + lane_base + TC_COL_GJ, v);
             tc_wait_ld();
-            const int64_t key = (int64_t)J * TC_TILE + r;
+            const int64_t key = (int64_t)Jr * TC_TILE + r;
             if (PROBE) {
                 for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
             } else if (key < a.n) {
@@ -375,17 +310,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
                                         __uint_as_float(v[4 * k4 + 3]) + __uint_as_float(v[19 + 4 * k4]));
             }
         }
-        // next key tile (every MMA that read the old one has completed: bar_g)
-        if (more) tc_store_z(xn, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO, smem + TC_OFF_ZJT);
+    };
+
+    for (int J = j_begin; J < j_end; ++J) {
+        const int k = J - j_begin, buf = k & 1;
+        const bool diag = J == I, more = J + 1 < j_end;
+        // the next key block's rows travel from HBM / L2 while this tile is processed
+        float xnext[4] = {0.f, 0.f, 0.f, 0.f};
+        if (more) tc_load_z(a, (int64_t)(J + 1) * TC_TILE, xnext);
+        tc_wait(bar_s, (uint32_t)(k & 1), a.err);
+        tc_fence_after();
+        // ---- compute phase: my row, 32 keys; runs while the tensor cores still work on the previous tile's gradients
+        const uint32_t s_col = (buf ? TC_COL_S1 : TC_COL_S0) + 32 * cq;
+        const int64_t key0 = (int64_t)J * TC_TILE + 32 * cq;
+        const bool ragged = ((int64_t)I * TC_TILE + TC_TILE > a.n) || ((int64_t)J * TC_TILE + TC_TILE > a.n);
+        uint32_t v[32], lo[32];
+        tc_ld32(tmem + lane_base + s_col, v);
+        tc_wait_ld();
+        float msum = 0.f, prod = 1.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const float x = __uint_as_float(v[e]);
+            if (PROBE) a.probe_S[(int64_t)r * TC_TILE + 32 * cq + e] = x;
+            float ex, rc;
+            const float t = -fabsf(x) * 1.4426950408889634f;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
+            float one_e = 1.0f + ex;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
+            float sg = (x >= 0.f) ? rc : ex * rc;
+            if (ragged) {
+                const bool ok = row_ok && (key0 + e < a.n);
+                sg = ok ? sg : 0.f;
+                one_e = ok ? one_e : 1.0f;
+            }
+            msum += fmaxf(x, 0.f);
+            prod *= one_e;
+            const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
+            v[e] = hb;                                             // sigma hi replaces the logit
+            lo[e] = __float_as_uint(sg - __uint_as_float(hb));
+        }
+        {
+            // sum softplus = sum max(x, 0) + ln prod (1 + e^-|x|): 32 factors in (1, 2] cannot overflow
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod));
+            const float tile_sum = msum + l2 * 0.6931471805599453f;
+            lacc += (double)(diag ? tile_sum : 2.f * tile_sum);
+        }
+        // ---- the previous tile's gradient MMAs must be done before sigma / Z^T are overwritten -------------------
+        if (k > 0) {
+            tc_wait(bar_g, (uint32_t)((k - 1) & 1), a.err);
+            tc_fence_after();
+            read_out(J - 1);
+        }
+        // ---- store phase: sigma_hi over S (TMEM), sigma_lo (TMEM), sigma^T hi / lo (shared), Z^T of this block,
+        //      [row][dim] tiles of the next block (S of this tile has completed: bar_s)
+        tc_st32(tmem + lane_base + s_col, v);
+        tc_st32(tmem + lane_base + TC_COL_SGL + 32 * cq, lo);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int c = 32 * cq + e;
+            const int off = (c >> 3) * TC_SGT_SBO + (c & 7) * 16;
+            *reinterpret_cast<uint32_t *>(sgt_hi_row + off) = v[e];
+            *reinterpret_cast<uint32_t *>(sgt_lo_row + off) = lo[e];
+        }
+        tc_store_zt(xcur, smem + TC_OFF_ZJT);
+        if (more) tc_store_z(xnext, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
+        tc_wait_st();
         tc_fence_before();
         tc_fence_async_smem();
         __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (more) issue_s(buf ^ 1);           // first: the next chain waits for this only
+            // gradients, sixteen K = 8 steps: sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi
+            const uint32_t a_hi = tmem + (buf ? TC_COL_S1 : TC_COL_S0), a_lo = tmem + TC_COL_SGL;
+            for (int ks = 0; ks < 16; ++ks) {      // G_I = sigma Z_J: A = sigma in TMEM (8 columns per step), B = Z_J^T tile
+                tc_mma_ts(tmem + TC_COL_GI, a_hi + 8 * ks, d_zjt + ks * 16, IDESC_G32, ks != 0);
+                tc_mma_ts(tmem + TC_COL_GI, a_lo + 8 * ks, d_zjt + ks * 16, IDESC_G16, 1);
+            }
+            if (!diag) {
+                for (int ks = 0; ks < 16; ++ks) {  // G_J = sigma^T Z_I: A = sigma^T tile (two 4-row groups per step), B = Z_I^T tile
+                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_hi + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G32, ks != 0);
+                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_lo + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G16, 1);
+                }
+            }
+            tc_commit(bar_g);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xcur[i] = xnext[i];
+    }
+    if (j_begin < j_end) {
+        tc_wait(bar_g, (uint32_t)((j_end - 1 - j_begin) & 1), a.err);
         tc_fence_after();
+        read_out(j_end - 1);
     }
 
     // ---- outputs of this CTA ---------------------------------------------------------------------------
     if (!PROBE) {
-        if (half == 0 && row_ok) {
+        if (cq == 0 && row_ok) {
             float4 *o = reinterpret_cast<float4 *>(a.dz_part + ((int64_t)blockIdx.y * a.n + row) * TC_D);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(gi[4 * k4], gi[4 * k4 + 1], gi[4 * k4 + 2], gi[4 * k4 + 3]);
