@@ -431,7 +431,9 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
     __shared__ double red[8];
     const int tid = threadIdx.x;
     const int sub = tid % LPR;
-    const int64_t i = (int64_t)blockIdx.x * RPB + tid / LPR;
+    // symmetric-half pass: the last row blocks sum the most partial slots -- they go first
+    const int64_t blk = dzT_part ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t i = blk * RPB + tid / LPR;
     const bool valid = i < n;
     const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
 
@@ -458,9 +460,20 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
         for (int s = 0; s < splits; ++s)
             f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
         // symmetric-half pass: the tiles (I, block of i), I < block, delivered sigma^T Z_I in slot I
-        if (dzT_part)
-            for (int64_t I = 0; I < i / 128; ++I)
-                f4_add(g, *reinterpret_cast<const float4 *>(dzT_part + (I * n + i) * D + sub * 4));
+        if (dzT_part) {
+            const int64_t nI = i / 128;
+            const float4 *p = reinterpret_cast<const float4 *>(dzT_part + i * D + sub * 4);
+            const int64_t step = n * D / 4;                      // float4 per slot
+            int64_t I = 0;
+            for (; I + 8 <= nI; I += 8) {                        // 8 independent loads in flight, summed in slot order
+                float4 t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __ldcs(p + (I + u) * step);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f4_add(g, t[u]);
+            }
+            for (; I < nI; ++I) f4_add(g, __ldcs(p + I * step));
+        }
         // x_ij = x_ji: (G + G^T) Zd doubles the dense term
         g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
     }

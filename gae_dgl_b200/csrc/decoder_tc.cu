@@ -31,6 +31,8 @@
 // Deterministic: the G_I partial of CTA (I, s) and the G_J partial of tile (I, J) have their own slots, summed
 // in fixed order by dec_finalize_kernel.  Waits are bounded (%globaltimer): on expiry an error word is set, the
 // loss becomes NaN and the kernel falls through -- a protocol fault is reported, never a hung GPU.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gae {
@@ -39,18 +41,21 @@ constexpr int TC_THREADS = 512;
 constexpr int TC_TILE = 128;
 constexpr int TC_D = 16;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr uint32_t TC_COL_S0 = 0, TC_COL_S1 = 128, TC_COL_SGL = 256, TC_COL_GI = 384, TC_COL_GJ = 416;   // sigma_hi overwrites S in place
+constexpr uint32_t TC_COL_S0 = 0, TC_COL_S1 = 128, TC_COL_SGL = 256;   // sigma_hi overwrites S in place
+constexpr uint32_t TC_COL_GI = 384, TC_COL_GJ = 448;                      // two 32-column accumulators each (one per issuing warp)
 // shared memory map (bytes)
 constexpr int TC_Z_BYTES = TC_TILE * TC_D * 4;             // [row][dim] tile, K = dim: LBO 128, SBO 512
-constexpr int TC_ZT_BYTES = 2 * TC_D * TC_TILE * 4;        // [hi dims | lo dims][row] tile, K = row: LBO 128, SBO 4096
-constexpr int TC_SGT_LBO = 144, TC_SGT_SBO = 32 * TC_SGT_LBO;   // sigma^T [key][row] tile, K = row
-constexpr int TC_SGT_BYTES = 16 * TC_SGT_SBO;              // 73 728
+constexpr int TC_ZT_BYTES = 2 * TC_D * TC_TILE * 4;        // Z_J^T: [hi dims | lo dims][row] tile, K = row: LBO 128, SBO 4096
+constexpr int TC_ZIT_SBO = 64 * 128;                       // Z_I^T: [n][k'] with k' = 2 row + h, K = k': LBO 128, SBO 8192
+constexpr int TC_ZIT_BYTES = 4 * TC_ZIT_SBO;               //   n < 16: Z_hi[row][n] for h = 0, 1 ; n >= 16: Z_lo[row][n - 16] for h = 0, zero for h = 1
+constexpr int TC_SGT_LBO = 144, TC_SGT_SBO = 64 * TC_SGT_LBO;   // sigma^T: [key][k'], (k' = 2 row) = hi, (2 row + 1) = lo
+constexpr int TC_SGT_BYTES = 16 * TC_SGT_SBO;              // 147 456
 constexpr int TC_OFF_ZI_HI = 0, TC_OFF_ZI_LO = TC_Z_BYTES, TC_OFF_ZJ_HI = 2 * TC_Z_BYTES, TC_OFF_ZJ_LO = 3 * TC_Z_BYTES;
-constexpr int TC_OFF_ZIT = 4 * TC_Z_BYTES, TC_OFF_ZJT = TC_OFF_ZIT + TC_ZT_BYTES;
-constexpr int TC_OFF_SGT_HI = TC_OFF_ZJT + TC_ZT_BYTES, TC_OFF_SGT_LO = TC_OFF_SGT_HI + TC_SGT_BYTES;
-constexpr int TC_OFF_BAR = TC_OFF_SGT_LO + TC_SGT_BYTES;
+constexpr int TC_OFF_ZIT = 4 * TC_Z_BYTES, TC_OFF_ZJT = TC_OFF_ZIT + TC_ZIT_BYTES;
+constexpr int TC_OFF_SGT = TC_OFF_ZJT + TC_ZT_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_SGT + TC_SGT_BYTES;
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 64;
-static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TC_SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
 
 struct TcArgs {
     const float *Zd;
@@ -62,6 +67,7 @@ struct TcArgs {
     uint32_t *err;        // bounded-wait expiry counter
     // probe (one tile, one CTA): raw S, G_I, G_J
     float *probe_S, *probe_GI, *probe_GJ;
+    long long *probe_clk;   // [8] clock64 stamps of thread 0 (probe only)
     int32_t probe_I, probe_J;
 };
 
@@ -107,6 +113,9 @@ __device__ __forceinline__ uint64_t tc_timer_ns() {
 __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t *err) {
     uint32_t done = 0;
     uint64_t t0 = 0;
+    // one lane polls (the spin would otherwise take issue slots from the warps still computing); __syncwarp
+    // orders the others behind its acquire
+    if ((threadIdx.x & 31) == 0)
     for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
@@ -137,6 +146,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
 }
@@ -199,6 +217,49 @@ __device__ __forceinline__ void tc_store_zt(const float (&x)[4], unsigned char *
     }
 }
 
+// Z_I^T for sigma^T Z_I with hi / lo of sigma interleaved along K (k' = 2 row + h):
+//   n < 16 : Z_hi[row][n] at h = 0 and h = 1      (sigma_hi Z_hi + sigma_lo Z_hi)
+//   n >= 16: Z_lo[row][n - 16] at h = 0, 0 at h = 1 (sigma_hi Z_lo)
+__device__ __forceinline__ void tc_store_zit(const float (&x)[4], unsigned char *t_tile) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, g = tid & 3;
+    const int toff = (r >> 1) * 128 + (r & 1) * 8;           // k' = 2 r: group k' / 4 = r / 2, position 2 (r % 2)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dim = 4 * g + k;
+        const uint32_t h = tc_tf32(x[k]);
+        const uint32_t l = tc_tf32(x[k] - __uint_as_float(h));
+        *reinterpret_cast<uint2 *>(t_tile + (dim >> 3) * TC_ZIT_SBO + (dim & 7) * 16 + toff) = make_uint2(h, h);
+        *reinterpret_cast<uint2 *>(t_tile + (2 + (dim >> 3)) * TC_ZIT_SBO + (dim & 7) * 16 + toff) = make_uint2(l, 0u);
+    }
+}
+
+// The element-wise chain on 32 logits of one row: v[e] becomes sigma_hi, lo[e] sigma_lo; msum / prod collect the loss.
+template <bool RAGGED>
+__device__ __forceinline__ void tc_chain(uint32_t (&v)[32], uint32_t (&lo)[32], float &msum, float &prod, bool row_ok,
+                                         int64_t keys_left) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const float x = __uint_as_float(v[e]);
+        float ex, rc;
+        const float t = fabsf(x) * -1.4426950408889634f;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
+        float one_e = 1.0f + ex;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
+        float sg = (x >= 0.f) ? rc : ex * rc;
+        if (RAGGED) {
+            const bool ok = row_ok && (e < keys_left);
+            sg = ok ? sg : 0.f;
+            one_e = ok ? one_e : 1.0f;
+        }
+        msum += fmaxf(x, 0.f);
+        prod *= one_e;
+        const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
+        v[e] = hb;
+        lo[e] = __float_as_uint(sg - __uint_as_float(hb));
+    }
+}
+
 template <bool PROBE>
 __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -221,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     // ---- set-up: barriers, TMEM, the stationary row block, the first key block ---------------------------
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_g) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(bar_g) : "memory");     // four issuing warps commit
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -236,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         float x[4];
         tc_load_z(a, (int64_t)I * TC_TILE, x);
         tc_store_z(x, smem + TC_OFF_ZI_HI, smem + TC_OFF_ZI_LO);
-        tc_store_zt(x, smem + TC_OFF_ZIT);
+        tc_store_zit(x, smem + TC_OFF_ZIT);
         if (j_begin < j_end) {
             tc_load_z(a, (int64_t)j_begin * TC_TILE, xcur);
             tc_store_z(xcur, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
@@ -255,9 +316,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
     // descriptors at K step 0 (thread 0 issues; the others never use them)
     const uint64_t d_zi_hi = tc_desc(tc_smem_u32(smem + TC_OFF_ZI_HI), 128, 512), d_zi_lo = tc_desc(tc_smem_u32(smem + TC_OFF_ZI_LO), 128, 512);
     const uint64_t d_zj_hi = tc_desc(tc_smem_u32(smem + TC_OFF_ZJ_HI), 128, 512), d_zj_lo = tc_desc(tc_smem_u32(smem + TC_OFF_ZJ_LO), 128, 512);
-    const uint64_t d_zit = tc_desc(tc_smem_u32(smem + TC_OFF_ZIT), 128, 4096), d_zjt = tc_desc(tc_smem_u32(smem + TC_OFF_ZJT), 128, 4096);
-    const uint64_t d_sgt_hi = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_HI), TC_SGT_LBO, TC_SGT_SBO);
-    const uint64_t d_sgt_lo = tc_desc(tc_smem_u32(smem + TC_OFF_SGT_LO), TC_SGT_LBO, TC_SGT_SBO);
+    const uint64_t d_zit = tc_desc(tc_smem_u32(smem + TC_OFF_ZIT), 128, TC_ZIT_SBO), d_zjt = tc_desc(tc_smem_u32(smem + TC_OFF_ZJT), 128, 4096);
+    const uint64_t d_sgt = tc_desc(tc_smem_u32(smem + TC_OFF_SGT), TC_SGT_LBO, TC_SGT_SBO);
 
     // S = Z_I Z_J^T into S buffer `buf`, split precision: hi hi + lo hi + hi lo, two K = 8 steps each
     auto issue_s = [&](int buf) {
@@ -270,44 +330,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         }
         tc_commit(bar_s);
     };
+    if (PROBE && tid == 0 && a.probe_clk) a.probe_clk[0] = clock64();
     if (tid == 0 && j_begin < j_end) issue_s(0);
+    if (PROBE && tid == 0 && a.probe_clk) a.probe_clk[1] = clock64();
 
     float gi[TC_D];
 #pragma unroll
     for (int k = 0; k < TC_D; ++k) gi[k] = 0.f;
-    double lacc = 0.0;
+    float lacc = 0.f;       // per thread: <= 32 tiles x 32 pairs of O(1) terms; fp64 only from the CTA sum on (DADD is slow here)
     const int r = 32 * q + lane;                                  // my row inside the tile
     const int64_t row = (int64_t)I * TC_TILE + r;                 // my query row (chain and G_I read-out)
     const bool row_ok = row < a.n;
     // where my row of sigma^T goes: K index = r; key c adds (c / 8) * SBO + (c % 8) * 16
-    unsigned char *sgt_hi_row = smem + TC_OFF_SGT_HI + (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
-    unsigned char *sgt_lo_row = smem + TC_OFF_SGT_LO + (r >> 2) * TC_SGT_LBO + (r & 3) * 4;
+    unsigned char *sgt_row = smem + TC_OFF_SGT + (r >> 1) * TC_SGT_LBO + (r & 1) * 8;      // k' = 2 r (hi), 2 r + 1 (lo)
 
     // gradient tiles of key block Jr leave TMEM: G_I into my registers (key quarter 0), G_J into its slot (quarter 1)
     auto read_out = [&](int Jr) {
+        // four 16-column pieces per product: {accumulator 0, 1} x {Z_hi, Z_lo columns}, summed in fp32
         if (cq == 0) {
-            uint32_t v[32];
-            tc_ld32(tmem + lane_base + TC_COL_GI, v);
-            tc_wait_ld();
+            float t[TC_D];
 #pragma unroll
-            for (int k = 0; k < TC_D; ++k) gi[k] += __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
+            for (int k = 0; k < TC_D; ++k) t[k] = 0.f;
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                uint32_t v[16];
+                tc_ld16(tmem + lane_base + TC_COL_GI + 16 * part, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < TC_D; ++k) t[k] += __uint_as_float(v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < TC_D; ++k) gi[k] += t[k];
             if (PROBE)
-                for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
+                for (int k = 0; k < TC_D; ++k) a.probe_GI[r * TC_D + k] = t[k];
         } else if (cq == 1 && Jr != I) {
-            uint32_t v[32];
-            tc_ld32(tmem + lane_base + TC_COL_GJ, v);
-            tc_wait_ld();
+            float t[TC_D];
+#pragma unroll
+            for (int k = 0; k < TC_D; ++k) t[k] = 0.f;
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                uint32_t v[16];
+                tc_ld16(tmem + lane_base + TC_COL_GJ + 16 * part, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < TC_D; ++k) t[k] += __uint_as_float(v[k]);
+            }
             const int64_t key = (int64_t)Jr * TC_TILE + r;
             if (PROBE) {
-                for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = __uint_as_float(v[k]) + __uint_as_float(v[TC_D + k]);
+                for (int k = 0; k < TC_D; ++k) a.probe_GJ[r * TC_D + k] = t[k];
             } else if (key < a.n) {
                 float4 *o = reinterpret_cast<float4 *>(a.dzT_part + ((int64_t)I * a.n + key) * TC_D);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    o[k4] = make_float4(__uint_as_float(v[4 * k4]) + __uint_as_float(v[16 + 4 * k4]),
-                                        __uint_as_float(v[4 * k4 + 1]) + __uint_as_float(v[17 + 4 * k4]),
-                                        __uint_as_float(v[4 * k4 + 2]) + __uint_as_float(v[18 + 4 * k4]),
-                                        __uint_as_float(v[4 * k4 + 3]) + __uint_as_float(v[19 + 4 * k4]));
+                for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(t[4 * k4], t[4 * k4 + 1], t[4 * k4 + 2], t[4 * k4 + 3]);
             }
         }
     };
@@ -320,6 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         if (more) tc_load_z(a, (int64_t)(J + 1) * TC_TILE, xnext);
         tc_wait(bar_s, (uint32_t)(k & 1), a.err);
         tc_fence_after();
+        if (PROBE && tid == 0 && a.probe_clk) a.probe_clk[2] = clock64();
         // ---- compute phase: my row, 32 keys; runs while the tensor cores still work on the previous tile's gradients
         const uint32_t s_col = (buf ? TC_COL_S1 : TC_COL_S0) + 32 * cq;
         const int64_t key0 = (int64_t)J * TC_TILE + 32 * cq;
@@ -327,34 +402,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
         uint32_t v[32], lo[32];
         tc_ld32(tmem + lane_base + s_col, v);
         tc_wait_ld();
+        if (PROBE)
+            for (int e = 0; e < 32; ++e) a.probe_S[(int64_t)r * TC_TILE + 32 * cq + e] = __uint_as_float(v[e]);
         float msum = 0.f, prod = 1.f;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const float x = __uint_as_float(v[e]);
-            if (PROBE) a.probe_S[(int64_t)r * TC_TILE + 32 * cq + e] = x;
-            float ex, rc;
-            const float t = -fabsf(x) * 1.4426950408889634f;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t));
-            float one_e = 1.0f + ex;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(one_e));
-            float sg = (x >= 0.f) ? rc : ex * rc;
-            if (ragged) {
-                const bool ok = row_ok && (key0 + e < a.n);
-                sg = ok ? sg : 0.f;
-                one_e = ok ? one_e : 1.0f;
-            }
-            msum += fmaxf(x, 0.f);
-            prod *= one_e;
-            const uint32_t hb = __float_as_uint(sg) & 0xffffe000u;
-            v[e] = hb;                                             // sigma hi replaces the logit
-            lo[e] = __float_as_uint(sg - __uint_as_float(hb));
-        }
+        if (ragged) tc_chain<true>(v, lo, msum, prod, row_ok, a.n - key0);
+        else tc_chain<false>(v, lo, msum, prod, true, 32);
         {
             // sum softplus = sum max(x, 0) + ln prod (1 + e^-|x|): 32 factors in (1, 2] cannot overflow
             float l2;
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod));
             const float tile_sum = msum + l2 * 0.6931471805599453f;
-            lacc += (double)(diag ? tile_sum : 2.f * tile_sum);
+            lacc += diag ? tile_sum : 2.f * tile_sum;
         }
         // ---- the previous tile's gradient MMAs must be done before sigma / Z^T are overwritten -------------------
         if (k > 0) {
@@ -369,39 +427,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
             const int c = 32 * cq + e;
-            const int off = (c >> 3) * TC_SGT_SBO + (c & 7) * 16;
-            *reinterpret_cast<uint32_t *>(sgt_hi_row + off) = v[e];
-            *reinterpret_cast<uint32_t *>(sgt_lo_row + off) = lo[e];
+            *reinterpret_cast<uint2 *>(sgt_row + (c >> 3) * TC_SGT_SBO + (c & 7) * 16) = make_uint2(v[e], lo[e]);
         }
+        if (PROBE && tid == 0 && a.probe_clk) a.probe_clk[3] = clock64();
         tc_store_zt(xcur, smem + TC_OFF_ZJT);
         if (more) tc_store_z(xnext, smem + TC_OFF_ZJ_HI, smem + TC_OFF_ZJ_LO);
         tc_wait_st();
         tc_fence_before();
         tc_fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        // Issuing an MMA costs its thread ~50 cycles (measured: 64 gradient MMAs = 3100 cycles from one thread), far more
+        // than these N = 32 / 16 MMAs run, so four warps -- one per scheduler -- issue in parallel, each into its own
+        // accumulator: G_I by K steps even / odd, G_J by halves of K'.  The next tile's S goes first (warp 0).
+        if (lane == 0 && warp < 4) {
             tc_fence_after();
-            if (more) issue_s(buf ^ 1);           // first: the next chain waits for this only
-            // gradients, sixteen K = 8 steps: sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi
-            const uint32_t a_hi = tmem + (buf ? TC_COL_S1 : TC_COL_S0), a_lo = tmem + TC_COL_SGL;
-            for (int ks = 0; ks < 16; ++ks) {      // G_I = sigma Z_J: A = sigma in TMEM (8 columns per step), B = Z_J^T tile
-                tc_mma_ts(tmem + TC_COL_GI, a_hi + 8 * ks, d_zjt + ks * 16, IDESC_G32, ks != 0);
-                tc_mma_ts(tmem + TC_COL_GI, a_lo + 8 * ks, d_zjt + ks * 16, IDESC_G16, 1);
-            }
-            if (!diag) {
-                for (int ks = 0; ks < 16; ++ks) {  // G_J = sigma^T Z_I: A = sigma^T tile (two 4-row groups per step), B = Z_I^T tile
-                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_hi + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G32, ks != 0);
-                    tc_mma_ss(tmem + TC_COL_GJ, d_sgt_lo + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G16, 1);
+            if (PROBE && warp == 0 && a.probe_clk) a.probe_clk[4] = clock64();
+            if (warp == 0 && more) issue_s(buf ^ 1);
+            if (warp < 2) {                          // G_I = sigma Z_J: A = sigma in TMEM (8 columns per step), B = Z_J^T tile
+                const uint32_t acc = tmem + TC_COL_GI + 32 * warp;
+                const uint32_t a_hi = tmem + (buf ? TC_COL_S1 : TC_COL_S0), a_lo = tmem + TC_COL_SGL;
+                for (int ks = warp; ks < 16; ks += 2) {      // sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi
+                    tc_mma_ts(acc, a_hi + 8 * ks, d_zjt + ks * 16, IDESC_G32, ks != warp);
+                    tc_mma_ts(acc, a_lo + 8 * ks, d_zjt + ks * 16, IDESC_G16, 1);
                 }
+            } else if (!diag) {                      // G_J = sigma^T Z_I over K' = 256 (hi / lo of sigma interleaved)
+                const int h = warp - 2;
+                const uint32_t acc = tmem + TC_COL_GJ + 32 * h;
+                for (int ks = 16 * h; ks < 16 * h + 16; ++ks)
+                    tc_mma_ss(acc, d_sgt + ks * (2 * TC_SGT_LBO / 16), d_zit + ks * 16, IDESC_G32, ks != 16 * h);
             }
             tc_commit(bar_g);
+            if (PROBE && warp == 0 && a.probe_clk) a.probe_clk[5] = clock64();
         }
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) xcur[i] = xnext[i];
     }
     if (j_begin < j_end) {
         tc_wait(bar_g, (uint32_t)((j_end - 1 - j_begin) & 1), a.err);
         tc_fence_after();
+        if (PROBE && tid == 0 && a.probe_clk) a.probe_clk[6] = clock64();
         read_out(j_end - 1);
     }
 
@@ -412,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_dense_tc_kernel(const TcArg
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(gi[4 * k4], gi[4 * k4 + 1], gi[4 * k4 + 2], gi[4 * k4 + 3]);
         }
-        double s = lacc;
+        double s = (double)lacc;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) red[warp] = s;
@@ -479,11 +544,26 @@ extern "C" int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t 
     TcArgs a{};
     a.Zd = Zd; a.ldz = ldz; a.n = n; a.d = d; a.T = T; a.splits = 1; a.err = err;
     a.probe_S = S; a.probe_GI = G_i; a.probe_GJ = G_j; a.probe_I = tile_i; a.probe_J = tile_j;
+    long long *clk = nullptr;
+    const bool want_clk = getenv("GAE_TC_PROBE_CLOCKS") != nullptr;
+    if (want_clk) {
+        GAE_CUDA(cudaMalloc(&clk, 8 * sizeof(long long)));
+        GAE_CUDA(cudaMemsetAsync(clk, 0, 8 * sizeof(long long), st));
+        a.probe_clk = clk;
+    }
     dec_dense_tc_kernel<true><<<1, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
     cudaError_t e = cudaGetLastError();
     uint32_t h = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h, err, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (want_clk && e == cudaSuccess) {
+        long long c[8];
+        e = cudaMemcpy(c, clk, sizeof(c), cudaMemcpyDeviceToHost);
+        // thread 0: S issued | S landed | chain done | gradient issue begins | ends | gradients landed (cycles after the S issue began)
+        fprintf(stderr, "[gae tile probe %d,%d] S issue %lld, S done %lld, chain done %lld, G issue start %lld, G issue end %lld, G done %lld\n",
+                tile_i, tile_j, c[1] - c[0], c[2] - c[0], c[3] - c[0], c[4] - c[0], c[5] - c[0], c[6] - c[0]);
+    }
+    if (clk) cudaFree(clk);
     cudaFree(err);
     if (e != cudaSuccess) {
         set_error("gae_decoder_tile_probe_f32: %s", cudaGetErrorString(e));
