@@ -13,6 +13,8 @@
 // the gradient (FP32 FFMA + MUFU bound: 2d FFMA + ex2 + lg2 + rcp per pair).  The j range
 // is split across CTAs; split partials are combined in fixed order by the finalize kernel,
 // which also adds the per-edge correction from CSR and CSR(A^T).  No atomics: deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gae {
@@ -35,6 +37,10 @@ struct DecConfig {
 int dec_tc_splits(int64_t n);
 cudaError_t dec_tc_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
                           double *loss_part, uint32_t *err, cudaStream_t st);
+// decoder_tc16.cu (dec_tc = 2, the default): fp16-split operands, issuing warp, pipelined over two TMEM buffer sets; same outputs
+int dec_tc16_splits(int64_t n);
+cudaError_t dec_tc16_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
+                            double *loss_part, uint32_t *err, cudaStream_t st);
 constexpr int64_t DEC_TC_MIN_ROWS = 512;
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
@@ -48,7 +54,8 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
         c->mma = false;
         c->JT = 128;
         c->nb = cdiv(n, 128);
-        c->splits = dec_tc_splits(n);
+        c->splits = tuning(T_DEC_TC) == 2 ? dec_tc16_splits(n) : dec_tc_splits(n);
+        if (tuning(T_DEC_SPLITS) > 0) c->splits = (int)std::min<int64_t>(tuning(T_DEC_SPLITS), c->nb);
         c->j_chunk = 0;
         c->fin_blocks = cdiv(n, 256 / (c->D / 4));
         return true;
@@ -416,6 +423,36 @@ dec_dense_mma_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d
     }
 }
 
+// Tensor-core (symmetric-half) paths: the partial sums of one row -- `splits` G_I slots and one G_J slot per row block
+// above the row's own -- folded into slot 0 of dz_part by ONE WARP PER ROW: lane = (slot group 0..7, float4 0..3), each
+// lane adds every 8th slot in slot order with four loads in flight, the eight groups meet in a fixed xor tree.
+// (dec_finalize_kernel used to walk the up to 155 slots from 4 lanes per row: 99 us at the Pubmed shape, all of it
+// load latency.)  Deterministic; the row's slot 0 is read and written by the same lanes.
+__global__ void __launch_bounds__(256) dec_slot_reduce_kernel(float *__restrict__ dz_part, int splits,
+                                                              const float *__restrict__ dzT_part, int64_t n) {
+    const int lane = threadIdx.x & 31, sub = lane & 3, sg = lane >> 2;
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int64_t step = n * 4;                                   // float4 per slot
+    float4 g = f4_zero();
+    const float4 *p = reinterpret_cast<const float4 *>(dz_part) + i * 4 + sub;
+    for (int s = sg; s < splits; s += 8) f4_add(g, __ldcs(p + s * step));
+    const float4 *q = reinterpret_cast<const float4 *>(dzT_part) + i * 4 + sub;
+    const int nI = (int)(i / 128);
+    int I = sg;
+    for (; I + 24 < nI; I += 32) {
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = __ldcs(q + (int64_t)(I + 8 * u) * step);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) f4_add(g, t[u]);
+    }
+    for (; I < nI; I += 8) f4_add(g, __ldcs(q + (int64_t)I * step));
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) f4_add(g, f4_shfl_xor(g, off));
+    if (sg == 0) reinterpret_cast<float4 *>(dz_part)[i * 4 + sub] = g;
+}
+
 // One lane group (D/4 lanes) per row: ordered split reduce + per-edge corrections.
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -424,16 +461,13 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
                     const int64_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t, float pw,
                     const float *__restrict__ dz_part, int splits, int mode, float inv_n2,
                     float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part,
-                    const int64_t *__restrict__ blk_lo, const int64_t *__restrict__ blk_hi,
-                    const float *__restrict__ dzT_part = nullptr) {
+                    const int64_t *__restrict__ blk_lo, const int64_t *__restrict__ blk_hi) {
     constexpr int LPR = D / 4;
     constexpr int RPB = 256 / LPR;
     __shared__ double red[8];
     const int tid = threadIdx.x;
     const int sub = tid % LPR;
-    // symmetric-half pass: the last row blocks sum the most partial slots -- they go first
-    const int64_t blk = dzT_part ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
-    const int64_t i = blk * RPB + tid / LPR;
+    const int64_t i = (int64_t)blockIdx.x * RPB + tid / LPR;
     const bool valid = i < n;
     const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
 
@@ -459,21 +493,6 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
     if (want_grad && valid && !blk_lo) {
         for (int s = 0; s < splits; ++s)
             f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
-        // symmetric-half pass: the tiles (I, block of i), I < block, delivered sigma^T Z_I in slot I
-        if (dzT_part) {
-            const int64_t nI = i / 128;
-            const float4 *p = reinterpret_cast<const float4 *>(dzT_part + i * D + sub * 4);
-            const int64_t step = n * D / 4;                      // float4 per slot
-            int64_t I = 0;
-            for (; I + 8 <= nI; I += 8) {                        // 8 independent loads in flight, summed in slot order
-                float4 t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __ldcs(p + (I + u) * step);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) f4_add(g, t[u]);
-            }
-            for (; I < nI; ++I) f4_add(g, __ldcs(p + I * step));
-        }
         // x_ij = x_ji: (G + G^T) Zd doubles the dense term
         g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
     }
@@ -546,6 +565,102 @@ dec_finalize_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            loss_part[blockIdx.x] = t;
+        }
+    }
+}
+
+// The same finalize step with ONE WARP PER ROW (the full-matrix decoder; the kernel above stays for the block-diagonal
+// variant): the warp's 32 / LPR lane groups take every G-th partial slot and every G-th edge of the row, and meet in a
+// fixed xor tree at the end -- deterministic, and a row's dependent chain (col -> Zd row -> dot -> MUFU) is deg / G
+// long instead of deg, with 8x (D = 16) the warps in flight.  Measured at the Pubmed shape: 82 us -> see profiles/.
+template <int D>
+__global__ void __launch_bounds__(256)
+dec_finalize_rows_kernel(const float *__restrict__ Zd, int64_t ldz, int64_t n, int d,
+                         const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                         const int64_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t, float pw,
+                         const float *__restrict__ dz_part, int splits, int mode, float inv_n2,
+                         float *__restrict__ dZ, int64_t ld_dz, double *__restrict__ loss_part) {
+    constexpr int LPR = D / 4;
+    constexpr int G = 32 / LPR;
+    __shared__ double red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+    const bool valid = i < n;                                     // warp-uniform
+    const bool want_loss = mode & GAE_DEC_LOSS, want_grad = mode & GAE_DEC_GRAD;
+
+    auto load_row = [&](int64_t r) -> float4 {
+        float4 v = f4_zero();
+        const float *p = Zd + r * ldz + sub * 4;
+        if (sub * 4 + 0 < d) v.x = __ldg(p + 0);
+        if (sub * 4 + 1 < d) v.y = __ldg(p + 1);
+        if (sub * 4 + 2 < d) v.z = __ldg(p + 2);
+        if (sub * 4 + 3 < d) v.w = __ldg(p + 3);
+        return v;
+    };
+    auto group_dot = [&](const float4 &a, const float4 &b) -> float {
+        float x = a.x * b.x;
+        x = fmaf(a.y, b.y, x); x = fmaf(a.z, b.z, x); x = fmaf(a.w, b.w, x);
+#pragma unroll
+        for (int off = 1; off < LPR; off <<= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        return x;
+    };
+
+    float4 g = f4_zero();
+    float lsum = 0.f;
+    if (valid) {
+        const float4 zi = load_row(i);
+        if (want_grad) {
+            for (int s = grp; s < splits; s += G)
+                f4_add(g, *reinterpret_cast<const float4 *>(dz_part + ((int64_t)s * n + i) * D + sub * 4));
+            // x_ij = x_ji: (G + G^T) Zd doubles the dense term
+            g.x *= 2.f; g.y *= 2.f; g.z *= 2.f; g.w *= 2.f;
+        }
+        {
+            const int64_t e0 = rowptr[i], len = rowptr[i + 1] - e0;
+            for (int64_t t = grp; t < len + grp; t += G) {      // same trip count for every group: the shuffles stay convergent
+                const bool on = t < len;
+                const float4 zj = on ? load_row(col[e0 + t]) : f4_zero();
+                const float x = group_dot(zi, zj);
+                float l, sg;
+                softplus_parts(x, l, sg);
+                if (on) {
+                    lsum += pw * (fmaxf(-x, 0.f) + l) - (fmaxf(x, 0.f) + l);
+                    f4_fma(g, -(pw * (1.f - sg) + sg), zj);
+                }
+            }
+        }
+        if (want_grad) {
+            const int64_t e0 = rowptr_t[i], len = rowptr_t[i + 1] - e0;
+            for (int64_t t = grp; t < len + grp; t += G) {
+                const bool on = t < len;
+                const float4 zj = on ? load_row(col_t[e0 + t]) : f4_zero();
+                const float x = group_dot(zi, zj);
+                float l, sg;
+                softplus_parts(x, l, sg);
+                if (on) f4_fma(g, -(pw * (1.f - sg) + sg), zj);
+            }
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1) f4_add(g, f4_shfl_xor(g, off));
+            if (grp == 0) {
+                float *o = dZ + i * ld_dz + sub * 4;
+                if (sub * 4 + 0 < d) o[0] = g.x * inv_n2;
+                if (sub * 4 + 1 < d) o[1] = g.y * inv_n2;
+                if (sub * 4 + 2 < d) o[2] = g.z * inv_n2;
+                if (sub * 4 + 3 < d) o[3] = g.w * inv_n2;
+            }
+        }
+    }
+    if (want_loss) {
+        double s = (valid && sub == 0) ? (double)lsum : 0.0;     // one lane per group holds the group's edges
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) red[warp] = s;
         __syncthreads();
         if (tid == 0) {
             double t = 0.0;
@@ -642,7 +757,7 @@ extern "C" int64_t gae_decoder_ws_bytes(int64_t n, int32_t d) {
     DecConfig c;
     if (n <= 0 || d <= 0 || !dec_config(n, d, &c)) return 0;
     const int64_t dz = align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256);
-    const int64_t lp = (int64_t)sizeof(double) * (c.nb * c.splits + c.fin_blocks);
+    const int64_t lp = (int64_t)sizeof(double) * (c.nb * c.splits + cdiv(n, 8));     // dense partials + one per finalize block
     const int64_t tc = c.tc ? align_up((int64_t)sizeof(float) * c.nb * n * c.D, 256) + 256 : 0;
     return dz + align_up(lp, 256) + tc;
 }
@@ -674,12 +789,14 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     double *loss_part = (double *)((char *)ws + align_up((int64_t)sizeof(float) * c.splits * n * c.D, 256));
     double *loss_part_edges = loss_part + c.nb * c.splits;
     float *dzT_part = nullptr;
+    const int64_t fin_rows_blocks = cdiv(n, 8);          // dec_finalize_rows_kernel: a warp per row, 8 rows per block
     if (c.tc) {
-        char *p = (char *)loss_part + align_up((int64_t)sizeof(double) * (c.nb * c.splits + c.fin_blocks), 256);
+        char *p = (char *)loss_part + align_up((int64_t)sizeof(double) * (c.nb * c.splits + fin_rows_blocks), 256);
         uint32_t *err = (uint32_t *)p;
         dzT_part = (float *)(p + 256);
-        GAE_CUDA(cudaMemsetAsync(err, 0, sizeof(uint32_t), st));
-        GAE_CUDA(dec_tc_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
+        GAE_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(uint32_t), st));      // expiry counter, max |Zd| bits
+        if (tuning(T_DEC_TC) == 2) GAE_CUDA(dec_tc16_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
+        else GAE_CUDA(dec_tc_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
     } else
     if (c.mma) GAE_CUDA(launch_dense_mma(c, mode, Zd, ldz, n, d, dz_part, loss_part, st));
     else if (c.D == 16 && c.R == 1) GAE_CUDA((launch_dense<16, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
@@ -688,21 +805,24 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
     else GAE_CUDA((launch_dense<64, 1>(c, mode, Zd, ldz, n, d, dz_part, loss_part, st)));
 
     const float inv_n2 = (float)(1.0 / ((double)n * (double)n));
+    int fin_splits = c.splits;
+    if (c.tc && want_grad) {      // fold the partial slots first (one warp per row); finalize then reads slot 0
+        dec_slot_reduce_kernel<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(dz_part, c.splits, dzT_part, n);
+        GAE_LAUNCH_CHECK();
+        fin_splits = 1;
+    }
     if (c.D == 16)
-        dec_finalize_kernel<16><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
-                                                                        nullptr, nullptr, dzT_part);
+        dec_finalize_rows_kernel<16><<<(unsigned)fin_rows_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight, dz_part,
+                                                                                fin_splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
     else if (c.D == 32)
-        dec_finalize_kernel<32><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
-                                                                        nullptr, nullptr);
+        dec_finalize_rows_kernel<32><<<(unsigned)fin_rows_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight, dz_part,
+                                                                                fin_splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
     else
-        dec_finalize_kernel<64><<<(unsigned)c.fin_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight,
-                                                                        dz_part, c.splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges,
-                                                                        nullptr, nullptr);
+        dec_finalize_rows_kernel<64><<<(unsigned)fin_rows_blocks, 256, 0, st>>>(Zd, ldz, n, d, rowptr, col, rowptr_t, col_t, pos_weight, dz_part,
+                                                                                fin_splits, mode, inv_n2, dZd_unit, ld_dz, loss_part_edges);
     GAE_LAUNCH_CHECK();
     if (want_loss) {
-        dec_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, c.nb * c.splits + c.fin_blocks,
+        dec_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, c.nb * c.splits + fin_rows_blocks,
                                                   1.0 / ((double)n * (double)n), loss);
         GAE_LAUNCH_CHECK();
     }

@@ -34,6 +34,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace gae {
 
@@ -70,113 +71,6 @@ struct TcArgs {
     long long *probe_clk;   // [8] clock64 stamps of thread 0 (probe only)
     int32_t probe_I, probe_J;
 };
-
-__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), LBO >> 4 at
-// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64)).  Advancing the start address by
-// b bytes is desc + (b >> 4).
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
-}
-// instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint64_t tc_timer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// bounded wait on an mbarrier phase
-__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t *err) {
-    uint32_t done = 0;
-    uint64_t t0 = 0;
-    // one lane polls (the spin would otherwise take issue slots from the warps still computing); __syncwarp
-    // orders the others behind its acquire
-    if ((threadIdx.x & 31) == 0)
-    for (uint32_t it = 0;; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if ((it & 255u) == 255u) {
-            const uint64_t now = tc_timer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) {   // 2 s
-                atomicAdd(err, 1u);
-                break;
-            }
-        }
-    }
-    __syncwarp();     // the .sync.aligned tcgen05 instructions that follow need the warp converged
-}
-#define TC_R32(v) \
-    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17], v[18], \
-        v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t tc_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 
 // Thread t of the CTA handles row t / 4, dims 4 (t % 4) .. + 4 of a 128-row block of Zd.
 __device__ __forceinline__ void tc_load_z(const TcArgs &a, int64_t row0, float (&x)[4]) {
@@ -528,6 +422,10 @@ cudaError_t dec_tc_launch(const float *Zd, int64_t ldz, int64_t n, int d, int sp
 
 }  // namespace gae
 
+namespace gae {
+cudaError_t dec_tc16_probe(const float *Zd, int64_t ldz, int64_t n, int d, int tile_i, int tile_j, float *S, float *G_i,
+                           float *G_j, uint32_t *err, cudaStream_t st);
+}
 using namespace gae;
 
 extern "C" int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t n, int32_t d, int32_t tile_i, int32_t tile_j,
@@ -539,8 +437,22 @@ extern "C" int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t 
     GAE_CUDA(cudaFuncSetAttribute(dec_dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *err = nullptr;
-    GAE_CUDA(cudaMalloc(&err, sizeof(uint32_t)));
-    GAE_CUDA(cudaMemsetAsync(err, 0, sizeof(uint32_t), st));
+    GAE_CUDA(cudaMalloc(&err, 2 * sizeof(uint32_t)));
+    GAE_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(uint32_t), st));
+    if (tuning(T_DEC_TC) == 2) {        // the fp16-split pipelined kernel (decoder_tc16.cu)
+        cudaError_t e2 = dec_tc16_probe(Zd, ldz, n, d, tile_i, tile_j, S, G_i, G_j, err, st);
+        uint32_t h2 = 0;
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(&h2, err, sizeof(h2), cudaMemcpyDeviceToHost, st);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+        cudaFree(err);
+        if (e2 != cudaSuccess) {
+            set_error("gae_decoder_tile_probe_f32: %s", cudaGetErrorString(e2));
+            return (int)e2;
+        }
+        count_launch(2);
+        *timeouts = (int32_t)h2;
+        return GAE_OK;
+    }
     TcArgs a{};
     a.Zd = Zd; a.ldz = ldz; a.n = n; a.d = d; a.T = T; a.splits = 1; a.err = err;
     a.probe_S = S; a.probe_GI = G_i; a.probe_GJ = G_j; a.probe_I = tile_i; a.probe_J = tile_j;

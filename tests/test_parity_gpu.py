@@ -276,25 +276,47 @@ def test_decoder_loss_and_grad_parity(cuda, n, d, e):
     assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
     scale = float(Zr.grad.abs().max())
     assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * scale
-    if d <= 16:     # both forms of the dense pass (tensor-core default, SIMT), every loss / gradient mode
-        default_mma = _lib.get_tuning("dec_mma")
-        assert default_mma == 1
+    if d <= 16:     # every form of the dense pass (tcgen05 fp16-split default, tcgen05 TF32, mma.sync, SIMT), every mode
+        default_mma, default_tc = _lib.get_tuning("dec_mma"), _lib.get_tuning("dec_tc")
+        assert default_mma == 1 and default_tc == 2
         try:
-            for mma in (0, 1):
+            for tc, mma in ((2, 1), (1, 1), (0, 1), (0, 0)):
+                _lib.set_tuning("dec_tc", tc)
                 _lib.set_tuning("dec_mma", mma)
                 for wl, wg in ((True, True), (True, False), (False, True)):
                     l2, dZ2 = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), pw,
                                               want_loss=wl, want_grad=wg)
                     if wl:
-                        assert abs(float(l2) - float(ref)) < TOL * abs(float(ref)), mma
+                        assert abs(float(l2) - float(ref)) < TOL * abs(float(ref)), (tc, mma)
                     if wg:
-                        assert float((dZ2.double().cpu() - Zr.grad).abs().max()) < TOL * scale, mma
+                        assert float((dZ2.double().cpu() - Zr.grad).abs().max()) < TOL * scale, (tc, mma)
         finally:
             _lib.set_tuning("dec_mma", default_mma)
+            _lib.set_tuning("dec_tc", default_tc)
     loss_only, none = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), None, None, pw, True, False)
     assert none is None and float(loss_only) == float(loss)
     X = ops.decoder_logits(Z.to(cuda))
     assert rel_err(X, Z.double() @ Z.double().t()) < TOL
+
+
+@pytest.mark.parametrize("zmul", [3.0e4, 40.0, 1.0e-3, 1.0e-6])
+def test_decoder_tc16_operand_scaling(cuda, zmul):
+    """The fp16-split tcgen05 pass scales its operands by a power of two taken from max|Zd|: embeddings far outside
+    fp16's range (and far below its normal range) must come out as exactly as O(1) ones (sparse-form fp64 oracle)."""
+    n, d, e = 900, 16, 4000
+    src, dst = random_graph(n, e, seed=7)
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    rt, ct = O.csr_transpose(rowptr, col)
+    g = torch.Generator().manual_seed(11)
+    Z = zmul * torch.randn(n, d, generator=g)
+    Zr = Z.double().requires_grad_(True)
+    ref = O.bce_loss_sparse_form(Zr, rowptr, col, 7.5)
+    ref.backward()
+    assert _lib.get_tuning("dec_tc") == 2
+    loss, dZ = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), 7.5,
+                               want_loss=True, want_grad=True)
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * float(Zr.grad.abs().max())
 
 
 def _load_weights(model, weights):
