@@ -332,13 +332,16 @@ def cuda_time_ms(fn, steps, stream):
 
 
 def decoder_roofline(dev, g, d=16, iters=20):
-    """Roofline of the dominant kernel of the small-graph train steps: the fused decoder (dense pass over all
-    N^2 pairs + finalize), timed ALONE with CUDA events on its launching stream.  Algorithmic work per launch
-    (DESIGN.md K5/K6): 4 N^2 d flop (S = Zd Zd^T and dZ = sigma(S) Zd; the reference's mm + BCE + backward do
-    more) and 2 N^2 MUFU ops (ex2 + rcp per pair; lg2 folded 64:1).  `bound` is "tensor": peak = half the
-    MEASURED bf16 rate (TF32 runs at half the bf16 rate; split precision triples the issued MMAs, which the
-    algorithmic count deliberately ignores).  The MUFU floor (16 ops/clk/SM x 148 SMs x max SM clock) is
-    reported beside it -- for d = 16 it is the tighter of the two."""
+    """Roofline of the dominant kernel of the small-graph train steps: the fused decoder (dense pass over the pairs
+    + partial-slot reduce + finalize + loss reduce), timed ALONE with CUDA events on its launching stream.
+    From 4096 rows (d <= 16) the dense pass is the tcgen05 symmetric-half kernel: it evaluates N^2 / 2 pairs, so the
+    algorithmic work per launch is 3 N^2 d flop (S over the upper triangle: N^2 d; G_I and G_J:
+    N^2 d each) and N^2 MUFU ops (ex2 + rcp per evaluated pair; lg2 folded 32:1); below that the mma.sync / SIMT forms
+    walk all N^2 pairs: 4 N^2 d flop, 2 N^2 MUFU ops.  `bound` is "tensor": peak = the MEASURED bf16 rate (fp16 operands
+    run at the bf16 rate; half of it for the TF32 mma.sync form; split precision triples the issued MMAs, which the
+    algorithmic count deliberately ignores).  Two tighter floors are reported beside it: the MUFU floor (16 ops/clk/SM
+    x 148 SMs x max SM clock) and, for the tcgen05 form, the measured MMA-issue floor (35 M = 128 MMAs per 128 x 128
+    tile at 74 / 98 / 110 cycles each whatever N is, tools/mma_bench.cu -> profiles/r02_mma_bench.log)."""
     from gae_dgl_b200 import ops
     n = g.number_of_nodes()
     c, t = g.csr(), g.csr_t()
@@ -353,7 +356,9 @@ def decoder_roofline(dev, g, d=16, iters=20):
         fn()
     torch.cuda.synchronize()
     ms = cuda_time_ms(fn, iters, st) / iters
-    flops = 4.0 * n * n * d
+    tc = d <= 16 and n >= 4096                      # DEC_TC_AUTO_ROWS (csrc/decoder.cu)
+    flops = (3.0 if tc else 4.0) * n * n * d
+    mufu = (1.0 if tc else 2.0) * n * n
     pk = {}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -361,14 +366,23 @@ def decoder_roofline(dev, g, d=16, iters=20):
             pk = json.load(f)
     bf16 = float(pk.get("bf16_tflops", 1590.0))
     sm_mhz = float(pk.get("sm_max_mhz", 1965.0))
-    peak = 0.5 * bf16
-    mufu_floor_ms = 2.0 * n * n / (16 * 148 * sm_mhz * 1e6) * 1e3
+    peak = bf16 if tc else 0.5 * bf16
+    mufu_floor_ms = mufu / (16 * 148 * sm_mhz * 1e6) * 1e3
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "kernel": "gae_decoder_bce_f32 (dense pass + finalize + loss reduce), timed alone", "ms": ms,
-            "algorithmic_flops": flops, "mufu_ops": 2.0 * n * n, "mufu_floor_ms": mufu_floor_ms,
-            "frac_mufu": mufu_floor_ms / ms,
-            "peak_source": ("0.5 x measured bf16 burst (MEASURED_PEAKS.json)" if pk else "0.5 x fallback bf16 1.59 PF")}
+    out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+           "kernel": "gae_decoder_bce_f32 (" + ("tcgen05 fp16-split symmetric-half dense pass + slot reduce" if tc else
+                                                "mma.sync TF32 dense pass" if d <= 16 else "SIMT dense pass")
+                     + " + finalize + loss reduce), timed alone",
+           "ms": ms, "algorithmic_flops": flops, "mufu_ops": mufu, "mufu_floor_ms": mufu_floor_ms,
+           "frac_mufu": mufu_floor_ms / ms,
+           "peak_source": (("" if tc else "0.5 x ") + "measured bf16 burst (MEASURED_PEAKS.json)" if pk else
+                           ("" if tc else "0.5 x ") + "fallback bf16 1.59 PF")}
+    if tc:
+        tiles = (n + 127) // 128
+        tiles = tiles * (tiles + 1) // 2
+        mma_floor_ms = tiles * (3 * 110 + 16 * 74 + 16 * 98) / (148 * sm_mhz * 1e6) * 1e3
+        out.update({"mma_issue_floor_ms": mma_floor_ms, "frac_mma_issue": mma_floor_ms / ms})
+    return out
 
 
 def pubmed_leg(dev, steps=100, warmup=5, name="pubmed"):

@@ -27,8 +27,9 @@ enum TuningIdx {
     T_DEC_MMA,           // decoder dense pass, d <= 16: 1 = both GEMMs as split-precision TF32 MMAs (default), 0 = SIMT FFMA2
     T_PUSH_UNROLL,       // halo push kernel: row steps in flight per lane group (4 or 8; registers 55 / 106)
     T_PUSH_STREAM_LD,    // halo push kernel: 1 = read the local rows with evict-first loads (ld.global.cs)
-    T_DEC_TC,            // decoder dense pass, d <= 16, n >= 512: tcgen05 / TMEM symmetric-half kernels -- 2 = fp16-split pipelined
-                         // form (decoder_tc16.cu, default), 1 = TF32 form (decoder_tc.cu), 0 = mma.sync / SIMT forms
+    T_DEC_TC,            // decoder dense pass, d <= 16: tcgen05 / TMEM symmetric-half kernels -- -1 = by size (default: the fp16-split
+                         // pipelined form from 4096 rows), 2 = that form (decoder_tc16.cu) from 512 rows, 1 = TF32 form
+                         // (decoder_tc.cu), 0 = mma.sync / SIMT forms
     T_COUNT
 };
 

@@ -30,7 +30,8 @@ struct DecConfig {
     int64_t j_chunk;   // key rows per split
     int64_t fin_blocks;
     bool mma;          // D = 16: both GEMMs on the tensor cores (dec_dense_mma_kernel)
-    bool tc;           // D = 16: tcgen05 / TMEM symmetric-half pass (decoder_tc.cu); nb = 128-row blocks then
+    bool tc;           // D = 16: tcgen05 / TMEM symmetric-half pass (decoder_tc16.cu / decoder_tc.cu); nb = 128-row blocks then
+    int tc_variant;    // 2 = fp16-split pipelined form, 1 = TF32 form
 };
 
 // decoder_tc.cu
@@ -41,7 +42,9 @@ cudaError_t dec_tc_launch(const float *Zd, int64_t ldz, int64_t n, int d, int sp
 int dec_tc16_splits(int64_t n);
 cudaError_t dec_tc16_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
                             double *loss_part, uint32_t *err, cudaStream_t st);
-constexpr int64_t DEC_TC_MIN_ROWS = 512;
+constexpr int64_t DEC_TC_MIN_ROWS = 512;      // an explicit dec_tc = 1 / 2 applies from here
+constexpr int64_t DEC_TC_AUTO_ROWS = 4096;    // dec_tc = -1 (default): tcgen05 form from here, mma.sync form below -- a CTA's TMEM / barrier
+                                              // set-up and drain cost about two tiles (measured: Cora shape, 22 x 22 tiles, 42 us vs 32 us)
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (d <= 16) { c->D = 16; c->R = tuning(T_DEC_ROWS) == 1 ? 1 : 2; }
@@ -49,12 +52,15 @@ static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     else if (d <= 64) { c->D = 64; c->R = 1; }
     else return false;
     c->mma = d <= 16 && tuning(T_DEC_MMA) != 0;
-    c->tc = d <= 16 && tuning(T_DEC_TC) != 0 && n >= DEC_TC_MIN_ROWS;
+    int tcv = tuning(T_DEC_TC);
+    if (tcv < 0) tcv = n >= DEC_TC_AUTO_ROWS ? 2 : 0;
+    c->tc = d <= 16 && tcv != 0 && n >= DEC_TC_MIN_ROWS;
+    c->tc_variant = tcv;
     if (c->tc) {
         c->mma = false;
         c->JT = 128;
         c->nb = cdiv(n, 128);
-        c->splits = tuning(T_DEC_TC) == 2 ? dec_tc16_splits(n) : dec_tc_splits(n);
+        c->splits = tcv == 2 ? dec_tc16_splits(n) : dec_tc_splits(n);
         if (tuning(T_DEC_SPLITS) > 0) c->splits = (int)std::min<int64_t>(tuning(T_DEC_SPLITS), c->nb);
         c->j_chunk = 0;
         c->fin_blocks = cdiv(n, 256 / (c->D / 4));
@@ -795,7 +801,7 @@ extern "C" int gae_decoder_bce_f32(const float *Zd, int64_t ldz, int64_t n, int3
         uint32_t *err = (uint32_t *)p;
         dzT_part = (float *)(p + 256);
         GAE_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(uint32_t), st));      // expiry counter, max |Zd| bits
-        if (tuning(T_DEC_TC) == 2) GAE_CUDA(dec_tc16_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
+        if (c.tc_variant == 2) GAE_CUDA(dec_tc16_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
         else GAE_CUDA(dec_tc_launch(Zd, ldz, n, d, c.splits, dz_part, dzT_part, loss_part, err, st));
     } else
     if (c.mma) GAE_CUDA(launch_dense_mma(c, mode, Zd, ldz, n, d, dz_part, loss_part, st));

@@ -439,7 +439,7 @@ extern "C" int gae_decoder_tile_probe_f32(const float *Zd, int64_t ldz, int64_t 
     uint32_t *err = nullptr;
     GAE_CUDA(cudaMalloc(&err, 2 * sizeof(uint32_t)));
     GAE_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(uint32_t), st));
-    if (tuning(T_DEC_TC) == 2) {        // the fp16-split pipelined kernel (decoder_tc16.cu)
+    if (tuning(T_DEC_TC) != 1) {        // the fp16-split pipelined kernel (decoder_tc16.cu), the default form
         cudaError_t e2 = dec_tc16_probe(Zd, ldz, n, d, tile_i, tile_j, S, G_i, G_j, err, st);
         uint32_t h2 = 0;
         if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(&h2, err, sizeof(h2), cudaMemcpyDeviceToHost, st);

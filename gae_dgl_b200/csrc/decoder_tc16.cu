@@ -73,11 +73,11 @@ struct HArgs {
 };
 
 // phase stamps (debug): P_* index prof[]
-enum { P_SETUP = 0, P_WAIT_S, P_LD, P_CHAIN, P_WAIT_G, P_READOUT, P_STORE, P_ARRIVE, P_TAIL, P_TILES, P_ISS_WAIT, P_ISS_ISSUE, P_CTAS, P_COUNT };
+enum { P_SETUP = 0, P_WAIT_S, P_LD, P_CHAIN, P_WAIT_G, P_READOUT, P_STORE, P_ARRIVE, P_TAIL, P_TILES, P_ISS_WAIT, P_ISS_ISSUE, P_CTAS, P_SIG_LAT, P_S_AGE, P_G_AGE, P_COUNT };
 #define H_STAMP(idx)                                                                  \
     if (prof_on) {                                                                    \
         const long long now_ = clock64();                                             \
-        atomicAdd(a.prof + (idx), (unsigned long long)(now_ - t_prev));               \
+        atomicAdd(a.prof + warp * P_COUNT + (idx), (unsigned long long)(now_ - t_prev)); \
         t_prev = now_;                                                                \
     }
 
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ double red[H_COMPUTE / 32];
+    __shared__ unsigned long long prof_last_arrive[2], prof_s_done[2], prof_g_done[2];   // GAE_TC_PROF only
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool issuer = warp == H_COMPUTE / 32;
     const int q = warp & 3, cq = (warp >> 2) & 3;      // TMEM lane quarter, key quarter of the tile
@@ -220,7 +221,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
     const int count = max(0, j_end - j_begin);
     const long long t_start = clock64();
     const uint32_t bar0 = tc_smem_u32(smem + H_OFF_BAR);
-    const uint32_t bar_sig = bar0 + 32;          // bar_s[b] = bar0 + 8 b, bar_g[b] = bar0 + 16 + 8 b  (b = tile & 1)
+    // bar_s[b] = bar0 + 8 b, bar_g[b] = bar0 + 16 + 8 b, bar_sig[b] = bar0 + 32 + 8 b  (b = tile & 1).  "sigma stored" needs
+    // two barriers: nothing in iteration k + 1 makes a fast warp wait for the issuing warp's round k (S(k + 1) and G(k - 1)
+    // were issued a round earlier), so it can arrive for tile k + 1 while a slow warp has not arrived for tile k -- on a
+    // single barrier that arrival would complete the wrong phase.  It cannot get two tiles ahead: S(k + 2) is issued only
+    // after every thread has arrived for tile k.
+    const uint32_t bar_sig = bar0 + 32;
 
     // power-of-two operand scale from max |Zd|: scaled magnitudes lie in [2^13, 2^14) at the top (fp16 overflows at
     // 65504, and its subnormals start 2^-14 -- 27 binades below the largest operand)
@@ -236,8 +242,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
 
     // ---- set-up: barriers, TMEM, the stationary row block, the first two key blocks ------------------------
     if (tid == 0) {
+        prof_last_arrive[0] = prof_last_arrive[1] = 0;
         for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * b) : "memory");   // S x 2, gradients x 2
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_sig), "r"(H_COMPUTE) : "memory");
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_sig + 8 * b), "r"(H_COMPUTE) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -263,10 +270,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const bool prof_on = a.prof != nullptr && lane == 0 && (warp == 0 || issuer);
+    const bool prof_on = a.prof != nullptr && lane == 0;
     if (prof_on) {
-        atomicAdd(a.prof + (issuer ? P_CTAS : P_SETUP), issuer ? 1ull : (unsigned long long)(clock64() - t_start));
-        if (!issuer) atomicAdd(a.prof + P_TILES, (unsigned long long)count);
+        atomicAdd(a.prof + warp * P_COUNT + (issuer ? P_CTAS : P_SETUP), issuer ? 1ull : (unsigned long long)(clock64() - t_start));
+        if (!issuer) atomicAdd(a.prof + warp * P_COUNT + P_TILES, (unsigned long long)count);
     }
     long long t_prev = clock64();
 
@@ -305,9 +312,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
         if (count > 1) issue_s(1);
         for (int k = 0; k < count; ++k) {
             const int b = k & 1;
-            tc_wait(bar_sig, (uint32_t)b, a.err);                     // sigma(k), Z_J^T(k), [row][dim] tiles of block k + 2 are in place
+            tc_wait(bar_sig + 8u * (uint32_t)b, (uint32_t)((k >> 1) & 1), a.err);   // sigma(k), Z_J^T(k), [row][dim] tiles of block k + 2 are in place
             tc_fence_after();
             H_STAMP(P_ISS_WAIT)
+            if (prof_on) {      // how long after the last arrival did this warp see the phase flip?
+                atomicAdd(a.prof + warp * P_COUNT + P_SIG_LAT, (unsigned long long)clock64() - prof_last_arrive[b]);
+                prof_last_arrive[b] = 0;
+            }
             const uint32_t sg = tmem + 128u * (uint32_t)b, acc = tmem + H_COL_ACC + H_ACC_STRIDE * (uint32_t)b;
             const uint64_t zjt = d_zjt + (uint64_t)(b * (H_ZJT_BYTES / 16)), sgt = d_sgt + (uint64_t)(b * (H_SGT_BYTES / 16));
             const bool diag = j_begin + k == I;
@@ -330,7 +341,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
                 tc_commit(bar0 + 16u + 8u * (uint32_t)b);
             }
             __syncwarp();
+            if (prof_on) prof_g_done[b] = (unsigned long long)clock64();          // issue end of G(k) ~ its completion (the issue blocks on the pipe)
             if (k + 2 < count) issue_s(k + 2);                        // into the buffer sigma(k) sits in: the pipe runs it after G_I(k)
+            if (prof_on) prof_s_done[b] = (unsigned long long)clock64();
             H_STAMP(P_ISS_ISSUE)
         }
     } else {
@@ -384,6 +397,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
             tc_wait(bar0 + 8u * (uint32_t)b, ph, a.err);
             tc_fence_after();
             H_STAMP(P_WAIT_S)
+            if (prof_on && k >= 2) atomicAdd(a.prof + warp * P_COUNT + P_S_AGE, (unsigned long long)clock64() - prof_s_done[b]);
             // ---- compute phase: my row, 32 keys
             const uint32_t s_addr = tmem + lane_base + 128u * (uint32_t)b + 32u * (uint32_t)cq;
             const int64_t key0 = (int64_t)J * H_TILE + 32 * cq;
@@ -428,7 +442,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
             H_STAMP(P_STORE)
             tc_fence_before();
             tc_fence_async_smem();
-            tc_arrive(bar_sig);
+            if (prof_on) atomicMax(&prof_last_arrive[b], (unsigned long long)clock64());
+            tc_arrive(bar_sig + 8u * (uint32_t)b);
             H_STAMP(P_ARRIVE)
             // ---- the previous tile's gradients, issued a whole iteration ago, leave TMEM (the MMAs of this tile go to the other
             //      accumulator set); after this wait the buffers of parity b ^ 1 are free for tile k + 1
@@ -436,6 +451,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
                 tc_wait(bar0 + 16u + 8u * (uint32_t)(b ^ 1), (uint32_t)(((k - 1) >> 1) & 1), a.err);
                 tc_fence_after();
                 H_STAMP(P_WAIT_G)
+                if (prof_on) atomicAdd(a.prof + warp * P_COUNT + P_G_AGE, (unsigned long long)clock64() - prof_g_done[b ^ 1]);
                 read_out(J - 1, b ^ 1);
                 H_STAMP(P_READOUT)
             }
@@ -514,22 +530,34 @@ cudaError_t dec_tc16_launch(const float *Zd, int64_t ldz, int64_t n, int d, int 
     a.dz_part = dz_part; a.dzT_part = dzT_part; a.loss_part = loss_part; a.err = err; a.absmax = err + 1;
     dim3 grid((unsigned)splits, (unsigned)a.T);
     static const bool prof = getenv("GAE_TC_PROF") != nullptr;      // debug: per-phase cycle totals, printed per launch (synchronises)
+    constexpr int NW = H_THREADS / 32;
     if (prof) {
-        e = cudaMalloc(&a.prof, P_COUNT * sizeof(unsigned long long));
+        e = cudaMalloc(&a.prof, NW * P_COUNT * sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
-        cudaMemsetAsync(a.prof, 0, P_COUNT * sizeof(unsigned long long), st);
+        cudaMemsetAsync(a.prof, 0, NW * P_COUNT * sizeof(unsigned long long), st);
     }
     dec_dense_tc16_kernel<false><<<grid, H_THREADS, H_SMEM_BYTES, st>>>(a);
     count_launch();
     if (prof) {
-        unsigned long long h[P_COUNT];
+        static unsigned long long h[NW * P_COUNT];
         cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         cudaFree(a.prof);
-        const double tiles = h[P_TILES] ? (double)h[P_TILES] : 1.0, ctas = h[P_CTAS] ? (double)h[P_CTAS] : 1.0;
-        fprintf(stderr, "[gae tc16 prof] ctas %llu tiles %llu | per CTA: setup %.0f tail %.0f | per tile (warp 0): wait_S %.0f ld %.0f chain %.0f wait_G %.0f readout %.0f store %.0f arrive %.0f | issuer per tile: wait %.0f issue %.0f\n",
-                h[P_CTAS], h[P_TILES], h[P_SETUP] / ctas, h[P_TAIL] / ctas, h[P_WAIT_S] / tiles, h[P_LD] / tiles, h[P_CHAIN] / tiles,
-                h[P_WAIT_G] / tiles, h[P_READOUT] / tiles, h[P_STORE] / tiles, h[P_ARRIVE] / tiles, h[P_ISS_WAIT] / tiles, h[P_ISS_ISSUE] / tiles);
+        const double tiles = h[P_TILES] ? (double)h[P_TILES] : 1.0, ctas = h[16 * P_COUNT + P_CTAS] ? (double)h[16 * P_COUNT + P_CTAS] : 1.0;
+        fprintf(stderr, "[gae tc16 prof] ctas %.0f tiles %.0f; cycles per tile (per CTA for setup / tail), lane 0 of each warp\n", ctas, tiles);
+        fprintf(stderr, "[gae tc16 prof] warp  setup   tail | wait_S     ld  chain  store arrive wait_G readout |  sum\n");
+        for (int w = 0; w < 16; ++w) {
+            const unsigned long long *r = h + w * P_COUNT;
+            const double sum = (double)(r[P_WAIT_S] + r[P_LD] + r[P_CHAIN] + r[P_STORE] + r[P_ARRIVE] + r[P_WAIT_G] + r[P_READOUT]) / tiles;
+            fprintf(stderr, "[gae tc16 prof] %4d %6.0f %6.0f | %6.0f %6.0f %6.0f %6.0f %6.0f %6.0f %7.0f | %5.0f\n", w, r[P_SETUP] / ctas, r[P_TAIL] / ctas,
+                    r[P_WAIT_S] / tiles, r[P_LD] / tiles, r[P_CHAIN] / tiles, r[P_STORE] / tiles, r[P_ARRIVE] / tiles, r[P_WAIT_G] / tiles,
+                    r[P_READOUT] / tiles, sum);
+        }
+        fprintf(stderr, "[gae tc16 prof] issuer per tile: wait %.0f issue %.0f; saw 'sigma stored' %.0f cycles after the last arrival\n",
+                h[16 * P_COUNT + P_ISS_WAIT] / tiles, h[16 * P_COUNT + P_ISS_ISSUE] / tiles, h[16 * P_COUNT + P_SIG_LAT] / tiles);
+        fprintf(stderr, "[gae tc16 prof] warp 0 / 5 / 10 / 15: S was issued %.0f / %.0f / %.0f / %.0f cycles before its wait returned, G %.0f / %.0f / %.0f / %.0f\n",
+                h[0 * P_COUNT + P_S_AGE] / tiles, h[5 * P_COUNT + P_S_AGE] / tiles, h[10 * P_COUNT + P_S_AGE] / tiles, h[15 * P_COUNT + P_S_AGE] / tiles,
+                h[0 * P_COUNT + P_G_AGE] / tiles, h[5 * P_COUNT + P_G_AGE] / tiles, h[10 * P_COUNT + P_G_AGE] / tiles, h[15 * P_COUNT + P_G_AGE] / tiles);
     }
     return cudaGetLastError();
 }

@@ -48,8 +48,10 @@ const char *gae_last_error_string(void);
  * streaming cp.async.bulk / LDGSTS), "spmm_unroll" (4), "spmm_block" (64), "spmm_cache" (0),
  * "spmm_rows_per_warp" (1), "spmm_stages" (2), "spmm_bins" (1), "spmm_seg_order" (1), "spmm_fused"
  * (-1 = automatic; 1 / 0: single-launch form of the binned forward on / off),
- * "dec_splits" (0 = auto), "dec_rows" (2), "dec_mma" (1: decoder dense pass on the tensor cores for
- * d <= 16; 0: SIMT), "push_unroll" (4), "push_stream_ld" (1).  The knobs are PER HOST THREAD.
+ * "dec_splits" (0 = auto), "dec_rows" (2), "dec_tc" (-1: by size -- the tcgen05 / TMEM fp16-split pass
+ * for d <= 16 from 4096 rows; 2 / 1: that pass / its TF32 predecessor from 512 rows; 0: never),
+ * "dec_mma" (1: below that, dense pass as mma.sync TF32 MMAs for d <= 16; 0: SIMT), "push_unroll" (4),
+ * "push_stream_ld" (1).  The knobs are PER HOST THREAD.
  * Results are independent of every knob up to fp32 summation order.
  * Unknown keys return GAE_ERR_INVALID_ARG.  gae_get_tuning returns the value or -1. */
 int gae_set_tuning(const char *key, int32_t value);

@@ -278,7 +278,7 @@ def test_decoder_loss_and_grad_parity(cuda, n, d, e):
     assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * scale
     if d <= 16:     # every form of the dense pass (tcgen05 fp16-split default, tcgen05 TF32, mma.sync, SIMT), every mode
         default_mma, default_tc = _lib.get_tuning("dec_mma"), _lib.get_tuning("dec_tc")
-        assert default_mma == 1 and default_tc == 2
+        assert default_mma == 1 and default_tc == -1
         try:
             for tc, mma in ((2, 1), (1, 1), (0, 1), (0, 0)):
                 _lib.set_tuning("dec_tc", tc)
@@ -312,9 +312,12 @@ def test_decoder_tc16_operand_scaling(cuda, zmul):
     Zr = Z.double().requires_grad_(True)
     ref = O.bce_loss_sparse_form(Zr, rowptr, col, 7.5)
     ref.backward()
-    assert _lib.get_tuning("dec_tc") == 2
-    loss, dZ = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), 7.5,
-                               want_loss=True, want_grad=True)
+    _lib.set_tuning("dec_tc", 2)
+    try:
+        loss, dZ = ops.decoder_bce(Z.to(cuda), rowptr.to(cuda), col.to(cuda), rt.to(cuda), ct.to(cuda), 7.5,
+                                   want_loss=True, want_grad=True)
+    finally:
+        _lib.set_tuning("dec_tc", -1)
     assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
     assert float((dZ.double().cpu() - Zr.grad).abs().max()) < TOL * float(Zr.grad.abs().max())
 
