@@ -3,27 +3,34 @@
 // G_I += sigma Z_J, G_J = sigma^T Z_I).  Reference: gae.py:71 + train_inductive.py:44-51.
 //
 // What differs from decoder_tc.cu (the TF32 form it supersedes; that kernel measured 359 us at the Pubmed shape with
-// the MUFU chain busy 23 % of the time -- everything else was un-overlapped latency):
+// the MUFU chain busy 23 % of the time -- everything else was un-overlapped latency; this one: 0.21 ms):
 //
 //  * Operands are split into TWO FP16 TERMS (hi = fp16(x), lo = fp16(x - hi): 11 + 11 significand bits, products
 //    exact in the fp32 accumulators, hi*hi + lo*hi + hi*lo as before -> the same ~2^-21 relative accuracy and the same
 //    1e-5 parity tests).  kind::f16 contracts K = 16 per instruction where kind::tf32 contracts 8, so a tile needs
-//    35 MMAs instead of 70 and half the tensor time; sigma_hi and sigma_lo of a row's 32 keys pack into the 32 TMEM
-//    columns its logits came from (in place: 128 columns per tile), and sigma^T in shared memory shrinks from
-//    144 KB to 72 KB.  FP16's range is handled by a power-of-two scale taken from max|Zd| (a tiny pre-pass) that puts
-//    the largest operand just below 2^14; it folds into constants the chain multiplies by anyway.
-//  * A DEDICATED ISSUING WARP (warp 16, one lane) owns every tcgen05.mma.  The 16 compute warps never issue and never
-//    meet at a CTA barrier inside the loop: they wait on mbarriers only (S landed / gradients landed) and signal
-//    "sigma stored" by arriving on one.
-//  * S is TRIPLE-BUFFERED in TMEM (3 x 128 columns; the gradient accumulators take 64): S(k+2) is issued when sigma(k)
-//    has been stored, a whole tile ahead of its use, and the gradient MMAs of tile k run under the chain of tile
-//    k+1.  The compute warps go chain -> read-out of the previous tile's gradients -> stores, back to back.
+//    35 MMAs instead of 70 (an M = 128 MMA costs 74 - 110 cycles whatever N is, tools/mma_bench.cu); sigma_hi and
+//    sigma_lo of a row's 32 keys pack into the 32 TMEM columns its logits came from (in place: 128 columns per tile),
+//    and sigma^T in shared memory shrinks from 144 KB to 72 KB -- room to double-buffer it.  FP16's range is handled by
+//    a power-of-two scale taken from max|Zd| (a tiny pre-pass) that puts the largest operand just below 2^14; it folds
+//    into constants the chain multiplies by anyway.
+//  * WARP ROLES.  16 compute warps do nothing but S -> sigma (tcgen05.ld, the ex2 / rcp chain, sigma back to TMEM in place
+//    and transposed to shared memory).  4 service warps (one per TMEM lane quarter; thread r = row r of a block) bring
+//    the Z_J operand tiles in (fp16 hi / lo [row][dim] tiles for S two tiles ahead, their transposes for sigma Z_J) and
+//    take the gradient accumulators out (G_I into registers, G_J to its global slot).  One issuing warp owns every
+//    tcgen05.mma, each batch under elect.sync (under `if (lane == 0)` ptxas wraps every MMA in an elect / vote loop).
+//    No CTA barrier inside the loop: mbarriers only ("S landed", "gradients landed", "sigma stored"), every lane
+//    polling (one polling lane + __syncwarp sees a flip ~370 cycles later, tools/bar_bench.cu).
+//  * TWO BUFFER SETS by tile parity (S / sigma in TMEM 2 x 128 columns, gradient accumulators 2 x 64, sigma^T, Z_J^T and
+//    the [row][dim] tiles in shared memory): at "sigma(k) stored" the issuing warp queues G(k) and then S(k + 2) -- into
+//    the buffer sigma(k) sits in; the pipe runs it after G_I(k) -- so S is a whole tile ahead of its use and the gradient
+//    MMAs of tile k run under the chain of tile k + 1; the service warps read them out one tile behind.
 //
 // Shared-memory operands: K-major, no swizzle, canonical 8-row x 16-byte core matrices (8 fp16 along K):
 //     off(m, k) = (m / 8) * SBO + (k / 8) * LBO + (m % 8) * 16 + (k % 8) * 2
 // TMEM A operand of sigma Z_J: lane = query row, one 32-bit column = two consecutive keys (low half first).
-// Deterministic: fixed slots per (I, split) and per tile, summed in fixed order by dec_finalize_kernel.  Waits are
+// Deterministic: fixed slots per (I, split) and per tile, summed in fixed order by dec_slot_reduce_kernel.  Waits are
 // bounded (%globaltimer): on expiry an error word is set and the loss becomes NaN -- never a hung GPU.
+// GAE_TC_PROF=1 prints per-warp cycles per phase after every launch (debug; profiles/r02_tc16_phase_profile.log).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -32,26 +39,27 @@
 
 namespace gae {
 
-constexpr int H_COMPUTE = 512;              // 16 compute warps
-constexpr int H_THREADS = 544;              // + the issuing warp
+constexpr int H_COMPUTE = 512;              // 16 compute warps: S -> sigma, nothing else
+constexpr int H_SERVICE = 128;              // 4 service warps (one per TMEM lane quarter): operand tiles in, gradient tiles out
+constexpr int H_THREADS = H_COMPUTE + H_SERVICE + 32;       // + the issuing warp
 constexpr int H_TILE = 128;
 constexpr int H_D = 16;
 constexpr uint32_t H_TMEM_COLS = 512;
 // TMEM: S buffers at 0 / 128 (tile k in buffer k & 1); two sets of gradient accumulators (tile k in set k & 1) at 256 /
-// 384, each: sigma_hi [Z_hi | Z_lo] (32 columns), sigma_lo Z_hi (16), sigma^T Z_I even / odd K steps (32 + 32).
+// 384, each: G_I = sigma_hi [Z_hi | Z_lo] + sigma_lo Z_hi on its first half (32 columns), G_J = sigma^T Z_I (32).
 // (Measured on this part, tools/mma_bench.cu: an M = 128 kind::f16 MMA occupies the pipe for ~74 cycles with A in TMEM
 // and ~98 with A in shared memory whatever N <= 64 is, 110 at N = 128, and separate accumulators change nothing -- the 35
 // MMAs of a tile cost ~3 100 cycles however they are arranged, so the schedule must keep them off the critical path.)
 constexpr uint32_t H_COL_ACC = 256, H_ACC_STRIDE = 128;
-constexpr uint32_t H_GIH = 0, H_GIL = 32, H_GJ0 = 48, H_GJ1 = 80;
+constexpr uint32_t H_GI = 0, H_GJ = 32;
 // shared memory map (bytes)
 constexpr int H_Z_BYTES = H_TILE * H_D * 2;                   // [row][dim] fp16 tile, K = dim: LBO 128, SBO 256
 constexpr int H_OFF_ZI_HI = 0, H_OFF_ZI_LO = H_Z_BYTES;
 constexpr int H_OFF_ZJ = 2 * H_Z_BYTES;                       // [buffer 0 / 1][hi | lo]
 constexpr int H_OFF_ZIT = H_OFF_ZJ + 4 * H_Z_BYTES;           // Z_I^T: [n = 32][k' = 2 row + h], LBO 128, SBO 4096
 constexpr int H_ZIT_SBO = 4096, H_ZIT_BYTES = 4 * H_ZIT_SBO;
-constexpr int H_OFF_ZJT = H_OFF_ZIT + H_ZIT_BYTES;            // Z_J^T x 2: [n = hi dims | lo dims][key], LBO 128, SBO 2048
-constexpr int H_ZJT_SBO = 2048, H_ZJT_BYTES = 4 * H_ZJT_SBO;
+constexpr int H_OFF_ZJT = H_OFF_ZIT + H_ZIT_BYTES;            // Z_J^T x 2: [n = hi dims | lo dims][key]; LBO 144: the 4 key groups of a warp on different banks
+constexpr int H_ZJT_LBO = 144, H_ZJT_SBO = 16 * H_ZJT_LBO, H_ZJT_BYTES = 4 * H_ZJT_SBO;
 constexpr int H_OFF_SGT = H_OFF_ZJT + 2 * H_ZJT_BYTES;        // sigma^T x 2: [key][k' = 2 row + h]; LBO 144 keeps the 32 rows of a warp on 32 banks
 constexpr int H_SGT_LBO = 144, H_SGT_SBO = 32 * H_SGT_LBO, H_SGT_BYTES = 16 * H_SGT_SBO;
 constexpr int H_OFF_BAR = H_OFF_SGT + 2 * H_SGT_BYTES;
@@ -73,7 +81,7 @@ struct HArgs {
 };
 
 // phase stamps (debug): P_* index prof[]
-enum { P_SETUP = 0, P_WAIT_S, P_LD, P_CHAIN, P_WAIT_G, P_READOUT, P_STORE, P_ARRIVE, P_TAIL, P_TILES, P_ISS_WAIT, P_ISS_ISSUE, P_CTAS, P_SIG_LAT, P_S_AGE, P_G_AGE, P_COUNT };
+enum { P_SETUP = 0, P_WAIT_S, P_LD, P_CHAIN, P_WAIT_G, P_READOUT, P_STORE, P_ARRIVE, P_TAIL, P_TILES, P_ISS_WAIT, P_ISS_ISSUE, P_CTAS, P_COUNT };
 #define H_STAMP(idx)                                                                  \
     if (prof_on) {                                                                    \
         const long long now_ = clock64();                                             \
@@ -96,13 +104,6 @@ __global__ void dec_absmax_kernel(const float *__restrict__ Zd, int64_t ldz, int
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-__device__ __forceinline__ uint32_t h_pack(__half lo16, __half hi16) {      // low half, high half
-    return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16);
-}
-__device__ __forceinline__ void h_split(float x, __half &hi, __half &lo) {
-    hi = __float2half_rn(x);
-    lo = __float2half_rn(x - __half2float(hi));
-}
 // two values at once through the packed converter (F2FP on the ALU pipe; the scalar cvt is an XU-pipe F2F)
 __device__ __forceinline__ void h_split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
@@ -110,59 +111,56 @@ __device__ __forceinline__ void h_split2(float x0, float x1, uint32_t &hi, uint3
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
 
-// Compute thread t handles row t / 4, dims 4 (t % 4) .. + 4 of a 128-row block of Zd.  The raw values stay in flight
-// until a store routine consumes them (the power-of-two scale zs is applied there, not at the load).
-__device__ __forceinline__ void h_load_z(const HArgs &a, int64_t row0, float (&x)[4]) {
-    const int tid = threadIdx.x;
-    const int64_t row = row0 + (tid >> 2);
-    const int k0 = (tid & 3) * 4;
+// Service thread r (one per row of a 128-row block) loads its whole row of Zd; the power-of-two scale zs is applied when
+// a store routine consumes the values, not at the load (the loads stay in flight meanwhile).
+__device__ __forceinline__ void h_load_row(const HArgs &a, int64_t row, float (&x)[H_D]) {
     const bool rv = row < a.n;
     const float *src = a.Zd + row * a.ldz;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = (rv && k0 + k < a.d) ? __ldg(src + k0 + k) : 0.f;
+    for (int k = 0; k < H_D; ++k) x[k] = (rv && k < a.d) ? __ldg(src + k) : 0.f;
 }
-// [row][dim] tiles (K = dim): hi and lo
-__device__ __forceinline__ void h_store_z(const float (&x)[4], float zs, unsigned char *hi_tile, unsigned char *lo_tile) {
-    const int tid = threadIdx.x;
-    const int r = tid >> 2, g = tid & 3;
-    uint32_t h01, l01, h23, l23;
-    h_split2(x[0] * zs, x[1] * zs, h01, l01);
-    h_split2(x[2] * zs, x[3] * zs, h23, l23);
-    const int off = (r >> 3) * 256 + (g >> 1) * 128 + (r & 7) * 16 + (g & 1) * 8;
-    *reinterpret_cast<uint2 *>(hi_tile + off) = make_uint2(h01, h23);
-    *reinterpret_cast<uint2 *>(lo_tile + off) = make_uint2(l01, l23);
+// hi / lo fp16 pairs of a row: h[p] = (x[2p], x[2p+1]) hi halves, l[p] the remainders
+__device__ __forceinline__ void h_split_row(const float (&x)[H_D], float zs, uint32_t (&h)[H_D / 2], uint32_t (&l)[H_D / 2]) {
+#pragma unroll
+    for (int p2 = 0; p2 < H_D / 2; ++p2) h_split2(x[2 * p2] * zs, x[2 * p2 + 1] * zs, h[p2], l[p2]);
 }
-// Z_J^T: [n][key] with n = dim (hi) or 16 + dim (lo), K = key
-__device__ __forceinline__ void h_store_zt(const float (&x)[4], float zs, unsigned char *t_tile) {
-    const int tid = threadIdx.x;
-    const int r = tid >> 2, g = tid & 3;
-    const int koff = (r >> 3) * 128 + (r & 7) * 2;
+// [row][dim] tiles (K = dim): row r owns two 16-byte core-matrix rows in each of the hi and lo tiles
+__device__ __forceinline__ void h_store_z_row(int r, const uint32_t (&h)[8], const uint32_t (&l)[8], unsigned char *hi_tile, unsigned char *lo_tile) {
+    const int off = (r >> 3) * 256 + (r & 7) * 16;
+    *reinterpret_cast<uint4 *>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(hi_tile + off + 128) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4 *>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(lo_tile + off + 128) = make_uint4(l[4], l[5], l[6], l[7]);
+}
+// the row's packed halves back from the [row][dim] tiles (the service thread wrote them itself two tiles ago)
+__device__ __forceinline__ void h_load_z_row(int r, const unsigned char *hi_tile, const unsigned char *lo_tile, uint32_t (&h)[8], uint32_t (&l)[8]) {
+    const int off = (r >> 3) * 256 + (r & 7) * 16;
+    const uint4 h0 = *reinterpret_cast<const uint4 *>(hi_tile + off), h1 = *reinterpret_cast<const uint4 *>(hi_tile + off + 128);
+    const uint4 l0 = *reinterpret_cast<const uint4 *>(lo_tile + off), l1 = *reinterpret_cast<const uint4 *>(lo_tile + off + 128);
+    h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+    l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+}
+// Z_J^T: [n][key] with n = dim (hi) or 16 + dim (lo), K = key = r
+__device__ __forceinline__ void h_store_zt_row(int r, const uint32_t (&h)[8], const uint32_t (&l)[8], unsigned char *t_tile) {
+    const int koff = (r >> 3) * H_ZJT_LBO + (r & 7) * 2;
 #pragma unroll
-    for (int k2 = 0; k2 < 2; ++k2) {
-        uint32_t h2, l2;
-        h_split2(x[2 * k2] * zs, x[2 * k2 + 1] * zs, h2, l2);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int dim = 4 * g + 2 * k2 + u;
-            *reinterpret_cast<unsigned short *>(t_tile + (dim >> 3) * H_ZJT_SBO + (dim & 7) * 16 + koff) = (unsigned short)(u ? h2 >> 16 : h2 & 0xffffu);
-            *reinterpret_cast<unsigned short *>(t_tile + (2 + (dim >> 3)) * H_ZJT_SBO + (dim & 7) * 16 + koff) = (unsigned short)(u ? l2 >> 16 : l2 & 0xffffu);
-        }
+    for (int dim = 0; dim < H_D; ++dim) {
+        const uint32_t hw = h[dim >> 1], lw = l[dim >> 1];
+        *reinterpret_cast<unsigned short *>(t_tile + (dim >> 3) * H_ZJT_SBO + (dim & 7) * 16 + koff) = (unsigned short)((dim & 1) ? hw >> 16 : hw & 0xffffu);
+        *reinterpret_cast<unsigned short *>(t_tile + (2 + (dim >> 3)) * H_ZJT_SBO + (dim & 7) * 16 + koff) = (unsigned short)((dim & 1) ? lw >> 16 : lw & 0xffffu);
     }
 }
 // Z_I^T for sigma^T Z_I with hi / lo of sigma interleaved along K (k' = 2 row + h):
 //   n < 16 : Z_hi[row][n] at h = 0 and h = 1        (sigma_hi Z_hi + sigma_lo Z_hi)
 //   n >= 16: Z_lo[row][n - 16] at h = 0, 0 at h = 1 (sigma_hi Z_lo)
-__device__ __forceinline__ void h_store_zit(const float (&x)[4], float zs, unsigned char *t_tile) {
-    const int tid = threadIdx.x;
-    const int r = tid >> 2, g = tid & 3;
+__device__ __forceinline__ void h_store_zit_row(int r, const uint32_t (&h)[8], const uint32_t (&l)[8], unsigned char *t_tile) {
     const int koff = (r >> 2) * 128 + (r & 3) * 4;          // k' = 2 r: group (2 r) / 8, position 2 ((2 r) % 8)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int dim = 4 * g + k;
-        __half h, l;
-        h_split(x[k] * zs, h, l);
-        *reinterpret_cast<uint32_t *>(t_tile + (dim >> 3) * H_ZIT_SBO + (dim & 7) * 16 + koff) = h_pack(h, h);
-        *reinterpret_cast<uint32_t *>(t_tile + (2 + (dim >> 3)) * H_ZIT_SBO + (dim & 7) * 16 + koff) = h_pack(l, __ushort_as_half(0));
+    for (int dim = 0; dim < H_D; ++dim) {
+        const uint32_t hv = (dim & 1) ? h[dim >> 1] >> 16 : h[dim >> 1] & 0xffffu;
+        const uint32_t lv = (dim & 1) ? l[dim >> 1] >> 16 : l[dim >> 1] & 0xffffu;
+        *reinterpret_cast<uint32_t *>(t_tile + (dim >> 3) * H_ZIT_SBO + (dim & 7) * 16 + koff) = hv | (hv << 16);
+        *reinterpret_cast<uint32_t *>(t_tile + (2 + (dim >> 3)) * H_ZIT_SBO + (dim & 7) * 16 + koff) = lv;
     }
 }
 
@@ -202,10 +200,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ double red[H_COMPUTE / 32];
-    __shared__ unsigned long long prof_last_arrive[2], prof_s_done[2], prof_g_done[2];   // GAE_TC_PROF only
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool issuer = warp == H_COMPUTE / 32;
-    const int q = warp & 3, cq = (warp >> 2) & 3;      // TMEM lane quarter, key quarter of the tile
+    const bool compute = warp < H_COMPUTE / 32, service = !compute && warp < (H_COMPUTE + H_SERVICE) / 32, issuer = !compute && !service;
+    const int q = warp & 3, cq = (warp >> 2) & 3;      // TMEM lane quarter (16 = 0 mod 4: also right for the service warps), key quarter
     // grid = (splits, T): row block 0 -- the longest runs -- is scheduled first, the short tail rows last
     const int I = PROBE ? a.probe_I : (int)blockIdx.y;
     const int split = PROBE ? 0 : (int)blockIdx.x;
@@ -242,9 +239,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
 
     // ---- set-up: barriers, TMEM, the stationary row block, the first two key blocks ------------------------
     if (tid == 0) {
-        prof_last_arrive[0] = prof_last_arrive[1] = 0;
         for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * b) : "memory");   // S x 2, gradients x 2
-        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_sig + 8 * b), "r"(H_COMPUTE) : "memory");
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_sig + 8 * b), "r"(H_COMPUTE + H_SERVICE) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -254,16 +250,24 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    float x0[4] = {0.f, 0.f, 0.f, 0.f}, x1[4] = {0.f, 0.f, 0.f, 0.f};      // my 4 values of key blocks k and k + 1
-    if (!issuer) {
-        float x[4];
-        h_load_z(a, (int64_t)I * H_TILE, x);                       // all three loads in flight before the first use
-        if (count > 0) h_load_z(a, (int64_t)j_begin * H_TILE, x0);
-        if (count > 1) h_load_z(a, (int64_t)(j_begin + 1) * H_TILE, x1);
-        h_store_z(x, zs, smem + H_OFF_ZI_HI, smem + H_OFF_ZI_LO);
-        h_store_zit(x, zs, smem + H_OFF_ZIT);
-        if (count > 0) h_store_z(x0, zs, smem + H_OFF_ZJ, smem + H_OFF_ZJ + H_Z_BYTES);
-        if (count > 1) h_store_z(x1, zs, smem + H_OFF_ZJ + 2 * H_Z_BYTES, smem + H_OFF_ZJ + 3 * H_Z_BYTES);
+    const int r = 32 * q + lane;                                  // my row inside a tile (compute: query row; service: query and key row)
+    if (service) {
+        float x[H_D], y0[H_D], y1[H_D];
+        h_load_row(a, (int64_t)I * H_TILE + r, x);                 // all three loads in flight before the first use
+        if (count > 0) h_load_row(a, (int64_t)j_begin * H_TILE + r, y0);
+        if (count > 1) h_load_row(a, (int64_t)(j_begin + 1) * H_TILE + r, y1);
+        uint32_t h[8], l[8];
+        h_split_row(x, zs, h, l);
+        h_store_z_row(r, h, l, smem + H_OFF_ZI_HI, smem + H_OFF_ZI_LO);
+        h_store_zit_row(r, h, l, smem + H_OFF_ZIT);
+        if (count > 0) {
+            h_split_row(y0, zs, h, l);
+            h_store_z_row(r, h, l, smem + H_OFF_ZJ, smem + H_OFF_ZJ + H_Z_BYTES);
+        }
+        if (count > 1) {
+            h_split_row(y1, zs, h, l);
+            h_store_z_row(r, h, l, smem + H_OFF_ZJ + 2 * H_Z_BYTES, smem + H_OFF_ZJ + 3 * H_Z_BYTES);
+        }
     }
     tc_fence_async_smem();
     tc_fence_before();
@@ -276,14 +280,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
         if (!issuer) atomicAdd(a.prof + warp * P_COUNT + P_TILES, (unsigned long long)count);
     }
     long long t_prev = clock64();
-
-    float gi[H_D];
-#pragma unroll
-    for (int k = 0; k < H_D; ++k) gi[k] = 0.f;
-    float lacc = 0.f;       // per thread: <= 32 tiles x 32 pairs of O(1) terms; fp64 only from the CTA sum on
-    const int r = 32 * q + lane;                                  // my row inside the tile
-    const int64_t row = (int64_t)I * H_TILE + r;                  // my query row (chain and G_I read-out)
-    const bool row_ok = row < a.n;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
 
     if (issuer) {
         // ================= the issuing warp: owns the tensor-core queue ===========================================
@@ -293,7 +290,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
         constexpr uint32_t IDESC_G16 = tc_idesc(128, 16, 0u);     // A x Z_hi
         const uint64_t d_zi_hi = tc_desc(tc_smem_u32(smem + H_OFF_ZI_HI), 128, 256), d_zi_lo = tc_desc(tc_smem_u32(smem + H_OFF_ZI_LO), 128, 256);
         const uint64_t d_zj0 = tc_desc(tc_smem_u32(smem + H_OFF_ZJ), 128, 256);     // + 256 per tile of [buffer][hi | lo]
-        const uint64_t d_zit = tc_desc(tc_smem_u32(smem + H_OFF_ZIT), 128, H_ZIT_SBO), d_zjt = tc_desc(tc_smem_u32(smem + H_OFF_ZJT), 128, H_ZJT_SBO);
+        const uint64_t d_zit = tc_desc(tc_smem_u32(smem + H_OFF_ZIT), 128, H_ZIT_SBO), d_zjt = tc_desc(tc_smem_u32(smem + H_OFF_ZJT), H_ZJT_LBO, H_ZJT_SBO);
         const uint64_t d_sgt = tc_desc(tc_smem_u32(smem + H_OFF_SGT), H_SGT_LBO, H_SGT_SBO);
         // S(k) = Z_I Z_J^T, split precision hi hi + lo hi + hi lo, one K = 16 step each
         auto issue_s = [&](int k) {
@@ -315,89 +312,122 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
             tc_wait(bar_sig + 8u * (uint32_t)b, (uint32_t)((k >> 1) & 1), a.err);   // sigma(k), Z_J^T(k), [row][dim] tiles of block k + 2 are in place
             tc_fence_after();
             H_STAMP(P_ISS_WAIT)
-            if (prof_on) {      // how long after the last arrival did this warp see the phase flip?
-                atomicAdd(a.prof + warp * P_COUNT + P_SIG_LAT, (unsigned long long)clock64() - prof_last_arrive[b]);
-                prof_last_arrive[b] = 0;
-            }
             const uint32_t sg = tmem + 128u * (uint32_t)b, acc = tmem + H_COL_ACC + H_ACC_STRIDE * (uint32_t)b;
             const uint64_t zjt = d_zjt + (uint64_t)(b * (H_ZJT_BYTES / 16)), sgt = d_sgt + (uint64_t)(b * (H_SGT_BYTES / 16));
             const bool diag = j_begin + k == I;
             if (tc_elect_one()) {
-                // G_I = sigma Z_J: A = sigma in TMEM (8 columns = 16 keys per step; hi at +0 / +8, lo at +16 / +24 of each 32),
-                // G_J = sigma^T Z_I over K' = 256 (hi / lo of sigma interleaved along K')
+                // G_I = sigma Z_J: A = sigma in TMEM (8 columns = 16 keys per step; hi at +0 / +8, lo at +16 / +24 of each 32);
+                // the sigma_lo Z_hi product lands on the first 16 columns of the same accumulator
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t a_hi = sg + 32u * (uint32_t)(i >> 1) + 8u * (uint32_t)(i & 1);
-                    tc_mma_ts_f16(acc + H_GIH, a_hi, zjt + i * 16, IDESC_G32, i != 0);
-                    tc_mma_ts_f16(acc + H_GIL, a_hi + 16u, zjt + i * 16, IDESC_G16, i != 0);
+                    tc_mma_ts_f16(acc + H_GI, a_hi, zjt + i * (2 * H_ZJT_LBO / 16), IDESC_G32, i != 0);
+                    tc_mma_ts_f16(acc + H_GI, a_hi + 16u, zjt + i * (2 * H_ZJT_LBO / 16), IDESC_G16, 1);
                 }
+                // G_J = sigma^T Z_I over K' = 256 (hi / lo of sigma interleaved along K')
                 if (!diag) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        tc_mma_ss_f16(acc + H_GJ0, sgt + (2 * i) * (2 * H_SGT_LBO / 16), d_zit + (2 * i) * 16, IDESC_G32, i != 0);
-                        tc_mma_ss_f16(acc + H_GJ1, sgt + (2 * i + 1) * (2 * H_SGT_LBO / 16), d_zit + (2 * i + 1) * 16, IDESC_G32, i != 0);
-                    }
+                    for (int i = 0; i < 16; ++i)
+                        tc_mma_ss_f16(acc + H_GJ, sgt + i * (2 * H_SGT_LBO / 16), d_zit + i * 16, IDESC_G32, i != 0);
                 }
                 tc_commit(bar0 + 16u + 8u * (uint32_t)b);
             }
             __syncwarp();
-            if (prof_on) prof_g_done[b] = (unsigned long long)clock64();          // issue end of G(k) ~ its completion (the issue blocks on the pipe)
             if (k + 2 < count) issue_s(k + 2);                        // into the buffer sigma(k) sits in: the pipe runs it after G_I(k)
-            if (prof_on) prof_s_done[b] = (unsigned long long)clock64();
             H_STAMP(P_ISS_ISSUE)
         }
-    } else {
-        // ================= the 16 compute warps =====================================================================
-        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-        const float c1 = -1.4426950408889634f * s2;
-        // where my row of sigma^T goes: k' = 2 r (hi), 2 r + 1 (lo): one 32-bit word; key c adds (c / 8) * SBO + (c % 8) * 16
-        unsigned char *sgt_row0 = smem + H_OFF_SGT + (4 * cq) * H_SGT_SBO + (r >> 2) * H_SGT_LBO + (r & 3) * 4;
-
-        // gradient tiles of key block Jr leave TMEM: G_I into my registers (key quarter 0), G_J into its slot (quarter 1)
+    } else if (service) {
+        // ================= the 4 service warps: operand tiles in, gradient tiles out ===============================
+        // Thread r: key row r of the Z_J blocks (its 16 values -> fp16 hi / lo tiles) and query row r / key row r of the
+        // gradient accumulators (TMEM lane r).
+        float gi[H_D];
+#pragma unroll
+        for (int k = 0; k < H_D; ++k) gi[k] = 0.f;
+        const int64_t row = (int64_t)I * H_TILE + r;
+        // gradient tiles of key block Jr leave TMEM: G_I into my registers, G_J into its slot
         auto read_out = [&](int Jr, int set) {
             const uint32_t acc = tmem + lane_base + H_COL_ACC + H_ACC_STRIDE * (uint32_t)set;
-            if (cq == 0) {
-                uint32_t g[32], gl[16];
-                tc_ld32(acc + H_GIH, g);
-                tc_ld16(acc + H_GIL, gl);
+            {
+                uint32_t g[32];
+                tc_ld32(acc + H_GI, g);
                 tc_wait_ld();
 #pragma unroll
                 for (int k = 0; k < H_D; ++k) {
-                    const float t = ((__uint_as_float(g[k]) + __uint_as_float(g[16 + k])) + __uint_as_float(gl[k])) * gs;
+                    const float t = (__uint_as_float(g[k]) + __uint_as_float(g[16 + k])) * gs;
                     gi[k] += t;
                     if (PROBE) a.probe_GI[r * H_D + k] = t;
                 }
-            } else if (cq == 1 && Jr != I) {
-                uint32_t g[32], g1[32];
-                tc_ld32(acc + H_GJ0, g);
-                tc_ld32(acc + H_GJ1, g1);
+            }
+            if (Jr != I) {
+                uint32_t g[32];
+                tc_ld32(acc + H_GJ, g);
                 tc_wait_ld();
-                float t[H_D];
 #pragma unroll
-                for (int k = 0; k < H_D; ++k)
-                    t[k] = ((__uint_as_float(g[k]) + __uint_as_float(g[16 + k])) + (__uint_as_float(g1[k]) + __uint_as_float(g1[16 + k]))) * gs;
+                for (int k = 0; k < H_D; ++k) g[k] = __float_as_uint((__uint_as_float(g[k]) + __uint_as_float(g[16 + k])) * gs);
                 const int64_t key = (int64_t)Jr * H_TILE + r;
                 if (PROBE) {
-                    for (int k = 0; k < H_D; ++k) a.probe_GJ[r * H_D + k] = t[k];
+                    for (int k = 0; k < H_D; ++k) a.probe_GJ[r * H_D + k] = __uint_as_float(g[k]);
                 } else if (key < a.n) {
-                    float4 *o = reinterpret_cast<float4 *>(a.dzT_part + ((int64_t)I * a.n + key) * H_D);
+                    uint4 *o = reinterpret_cast<uint4 *>(a.dzT_part + ((int64_t)I * a.n + key) * H_D);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(t[4 * k4], t[4 * k4 + 1], t[4 * k4 + 2], t[4 * k4 + 3]);
+                    for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_uint4(g[4 * k4], g[4 * k4 + 1], g[4 * k4 + 2], g[4 * k4 + 3]);
                 }
             }
         };
-
+        float y[H_D];                                              // my key row of block k + 2, in flight from L2
+        if (2 < count) h_load_row(a, (int64_t)(j_begin + 2) * H_TILE + r, y);
+        for (int k = 0; k < count; ++k) {
+            const int J = j_begin + k, b = k & 1;
+            const uint32_t ph = (uint32_t)((k >> 1) & 1);
+            unsigned char *zj_hi = smem + H_OFF_ZJ + b * 2 * H_Z_BYTES, *zj_lo = zj_hi + H_Z_BYTES;
+            uint32_t h[8], l[8];
+            // Z_J^T(k) from the [row][dim] tiles of block k (same halves, transposed).  Its buffer b was last read by the
+            // gradient MMAs of tile k - 2: waited for in iteration k - 1 (below).
+            h_load_z_row(r, zj_hi, zj_lo, h, l);
+            h_store_zt_row(r, h, l, smem + H_OFF_ZJT + b * H_ZJT_BYTES);
+            if (k + 2 < count) {
+                tc_wait(bar0 + 8u * (uint32_t)b, ph, a.err);      // the [row][dim] buffer b was read by S(k): it has landed
+                h_split_row(y, zs, h, l);
+                h_store_z_row(r, h, l, zj_hi, zj_lo);
+            }
+            tc_fence_before();       // orders the read-out of iteration k - 1 (tcgen05.ld, waited) before the arrival
+            tc_fence_async_smem();
+            tc_arrive(bar_sig + 8u * (uint32_t)b);
+            H_STAMP(P_STORE)
+            if (k + 3 < count) h_load_row(a, (int64_t)(J + 3) * H_TILE + r, y);      // next iteration's block, under the wait below
+            // the previous tile's gradients (the MMAs of this tile go to the other accumulator set)
+            if (k > 0) {
+                tc_wait(bar0 + 16u + 8u * (uint32_t)(b ^ 1), (uint32_t)(((k - 1) >> 1) & 1), a.err);
+                tc_fence_after();
+                H_STAMP(P_WAIT_G)
+                read_out(J - 1, b ^ 1);
+                H_STAMP(P_READOUT)
+            }
+        }
+        if (count > 0) {
+            tc_wait(bar0 + 16u + 8u * (uint32_t)((count - 1) & 1), (uint32_t)(((count - 1) >> 1) & 1), a.err);
+            tc_fence_after();
+            read_out(j_end - 1, (count - 1) & 1);
+        }
+        if (!PROBE && row < a.n) {
+            float4 *o = reinterpret_cast<float4 *>(a.dz_part + ((int64_t)split * a.n + row) * H_D);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(gi[4 * k4], gi[4 * k4 + 1], gi[4 * k4 + 2], gi[4 * k4 + 3]);
+        }
+    } else {
+        // ================= the 16 compute warps: S -> sigma =========================================================
+        const float c1 = -1.4426950408889634f * s2;
+        float lacc = 0.f;       // per thread: <= 40 tiles x 32 pairs of O(1) terms; fp64 only from the CTA sum on
+        const bool row_ok = (int64_t)I * H_TILE + r < a.n;
+        // where my row of sigma^T goes: k' = 2 r (hi), 2 r + 1 (lo): one 32-bit word; key c adds (c / 8) * SBO + (c % 8) * 16
+        unsigned char *sgt_row0 = smem + H_OFF_SGT + (4 * cq) * H_SGT_SBO + (r >> 2) * H_SGT_LBO + (r & 3) * 4;
         for (int k = 0; k < count; ++k) {
             const int J = j_begin + k, b = k & 1;
             const uint32_t ph = (uint32_t)((k >> 1) & 1);
             const bool diag = J == I;
-            // the rows of key block k + 2 travel from L2 while this tile is processed
-            float x2[4] = {0.f, 0.f, 0.f, 0.f};
-            if (k + 2 < count) h_load_z(a, (int64_t)(J + 2) * H_TILE, x2);
             tc_wait(bar0 + 8u * (uint32_t)b, ph, a.err);
             tc_fence_after();
             H_STAMP(P_WAIT_S)
-            if (prof_on && k >= 2) atomicAdd(a.prof + warp * P_COUNT + P_S_AGE, (unsigned long long)clock64() - prof_s_done[b]);
             // ---- compute phase: my row, 32 keys
             const uint32_t s_addr = tmem + lane_base + 128u * (uint32_t)b + 32u * (uint32_t)cq;
             const int64_t key0 = (int64_t)J * H_TILE + 32 * cq;
@@ -419,60 +449,32 @@ __global__ void __launch_bounds__(H_THREADS, 1) dec_dense_tc16_kernel(const HArg
                 lacc += diag ? tile_sum : 2.f * tile_sum;
             }
             H_STAMP(P_CHAIN)
-            // ---- store phase: sigma hi | lo over my 32 columns of S (TMEM), sigma^T and Z_J^T into the buffers of parity b
-            //      (last read by the gradient MMAs of tile k - 2: waited for at the end of the previous iteration), the
-            //      [row][dim] tiles of block k + 2 (their buffer was read by S(k), which has landed)
+            // ---- store phase: sigma hi | lo over my 32 columns of S (TMEM, in place), sigma^T into buffer b -- last read by
+            //      the gradient MMAs of tile k - 2, which landed long ago (their barrier is checked, not waited on in practice)
             {
                 uint32_t tw[32];
 #pragma unroll
-                for (int p = 0; p < 16; ++p) {
-                    tw[p] = __byte_perm(v[2 * p], v[2 * p + 1], 0x5410);          // sigma_hi of keys 2p, 2p + 1
-                    tw[16 + p] = __byte_perm(v[2 * p], v[2 * p + 1], 0x7632);     // sigma_lo
+                for (int p2 = 0; p2 < 16; ++p2) {
+                    tw[p2] = __byte_perm(v[2 * p2], v[2 * p2 + 1], 0x5410);          // sigma_hi of keys 2p, 2p + 1
+                    tw[16 + p2] = __byte_perm(v[2 * p2], v[2 * p2 + 1], 0x7632);     // sigma_lo
                 }
                 tc_st32(s_addr, tw);
             }
+            if (k >= 2) tc_wait(bar0 + 16u + 8u * (uint32_t)b, (uint32_t)(((k - 2) >> 1) & 1), a.err);
+            H_STAMP(P_WAIT_G)
             {
                 unsigned char *sgt_row = sgt_row0 + b * H_SGT_BYTES;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) *reinterpret_cast<uint32_t *>(sgt_row + (e >> 3) * H_SGT_SBO + (e & 7) * 16) = v[e];
             }
-            h_store_zt(x0, zs, smem + H_OFF_ZJT + b * H_ZJT_BYTES);
-            if (k + 2 < count) h_store_z(x2, zs, smem + H_OFF_ZJ + b * 2 * H_Z_BYTES, smem + H_OFF_ZJ + (b * 2 + 1) * H_Z_BYTES);
             tc_wait_st();
             H_STAMP(P_STORE)
             tc_fence_before();
             tc_fence_async_smem();
-            if (prof_on) atomicMax(&prof_last_arrive[b], (unsigned long long)clock64());
             tc_arrive(bar_sig + 8u * (uint32_t)b);
             H_STAMP(P_ARRIVE)
-            // ---- the previous tile's gradients, issued a whole iteration ago, leave TMEM (the MMAs of this tile go to the other
-            //      accumulator set); after this wait the buffers of parity b ^ 1 are free for tile k + 1
-            if (k > 0) {
-                tc_wait(bar0 + 16u + 8u * (uint32_t)(b ^ 1), (uint32_t)(((k - 1) >> 1) & 1), a.err);
-                tc_fence_after();
-                H_STAMP(P_WAIT_G)
-                if (prof_on) atomicAdd(a.prof + warp * P_COUNT + P_G_AGE, (unsigned long long)clock64() - prof_g_done[b ^ 1]);
-                read_out(J - 1, b ^ 1);
-                H_STAMP(P_READOUT)
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                x0[i] = x1[i];
-                x1[i] = x2[i];
-            }
         }
-        if (count > 0) {
-            tc_wait(bar0 + 16u + 8u * (uint32_t)((count - 1) & 1), (uint32_t)(((count - 1) >> 1) & 1), a.err);
-            tc_fence_after();
-            read_out(j_end - 1, (count - 1) & 1);
-        }
-        // ---- outputs of this CTA -------------------------------------------------------------------------------
         if (!PROBE) {
-            if (cq == 0 && row_ok) {
-                float4 *o = reinterpret_cast<float4 *>(a.dz_part + ((int64_t)split * a.n + row) * H_D);
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) o[k4] = make_float4(gi[4 * k4], gi[4 * k4 + 1], gi[4 * k4 + 2], gi[4 * k4 + 3]);
-            }
             double s = (double)lacc;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -543,21 +545,18 @@ cudaError_t dec_tc16_launch(const float *Zd, int64_t ldz, int64_t n, int d, int 
         cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         cudaFree(a.prof);
-        const double tiles = h[P_TILES] ? (double)h[P_TILES] : 1.0, ctas = h[16 * P_COUNT + P_CTAS] ? (double)h[16 * P_COUNT + P_CTAS] : 1.0;
-        fprintf(stderr, "[gae tc16 prof] ctas %.0f tiles %.0f; cycles per tile (per CTA for setup / tail), lane 0 of each warp\n", ctas, tiles);
-        fprintf(stderr, "[gae tc16 prof] warp  setup   tail | wait_S     ld  chain  store arrive wait_G readout |  sum\n");
-        for (int w = 0; w < 16; ++w) {
+        const int iw = NW - 1;
+        const double tiles = h[P_TILES] ? (double)h[P_TILES] : 1.0, ctas = h[iw * P_COUNT + P_CTAS] ? (double)h[iw * P_COUNT + P_CTAS] : 1.0;
+        fprintf(stderr, "[gae tc16 prof] ctas %.0f tiles %.0f; cycles per tile (per CTA for setup / tail), lane 0 of each warp; warps 16-19 = service\n", ctas, tiles);
+        fprintf(stderr, "[gae tc16 prof] warp  setup   tail | wait_S     ld  chain wait_G  store arrive readout |  sum\n");
+        for (int w = 0; w < iw; ++w) {
             const unsigned long long *r = h + w * P_COUNT;
             const double sum = (double)(r[P_WAIT_S] + r[P_LD] + r[P_CHAIN] + r[P_STORE] + r[P_ARRIVE] + r[P_WAIT_G] + r[P_READOUT]) / tiles;
             fprintf(stderr, "[gae tc16 prof] %4d %6.0f %6.0f | %6.0f %6.0f %6.0f %6.0f %6.0f %6.0f %7.0f | %5.0f\n", w, r[P_SETUP] / ctas, r[P_TAIL] / ctas,
-                    r[P_WAIT_S] / tiles, r[P_LD] / tiles, r[P_CHAIN] / tiles, r[P_STORE] / tiles, r[P_ARRIVE] / tiles, r[P_WAIT_G] / tiles,
+                    r[P_WAIT_S] / tiles, r[P_LD] / tiles, r[P_CHAIN] / tiles, r[P_WAIT_G] / tiles, r[P_STORE] / tiles, r[P_ARRIVE] / tiles,
                     r[P_READOUT] / tiles, sum);
         }
-        fprintf(stderr, "[gae tc16 prof] issuer per tile: wait %.0f issue %.0f; saw 'sigma stored' %.0f cycles after the last arrival\n",
-                h[16 * P_COUNT + P_ISS_WAIT] / tiles, h[16 * P_COUNT + P_ISS_ISSUE] / tiles, h[16 * P_COUNT + P_SIG_LAT] / tiles);
-        fprintf(stderr, "[gae tc16 prof] warp 0 / 5 / 10 / 15: S was issued %.0f / %.0f / %.0f / %.0f cycles before its wait returned, G %.0f / %.0f / %.0f / %.0f\n",
-                h[0 * P_COUNT + P_S_AGE] / tiles, h[5 * P_COUNT + P_S_AGE] / tiles, h[10 * P_COUNT + P_S_AGE] / tiles, h[15 * P_COUNT + P_S_AGE] / tiles,
-                h[0 * P_COUNT + P_G_AGE] / tiles, h[5 * P_COUNT + P_G_AGE] / tiles, h[10 * P_COUNT + P_G_AGE] / tiles, h[15 * P_COUNT + P_G_AGE] / tiles);
+        fprintf(stderr, "[gae tc16 prof] issuer per tile: wait %.0f issue %.0f\n", h[iw * P_COUNT + P_ISS_WAIT] / tiles, h[iw * P_COUNT + P_ISS_ISSUE] / tiles);
     }
     return cudaGetLastError();
 }

@@ -42,13 +42,12 @@ __device__ __forceinline__ uint64_t tc_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// bounded wait on an mbarrier phase
+// bounded wait on an mbarrier phase.  EVERY lane polls: with one polling lane and the other 31 parked at __syncwarp the
+// warp saw a phase flip ~510 cycles after the signal, with all lanes in try_wait 143 (tools/bar_bench.cu,
+// profiles/r02_bar_bench.log) -- try_wait suspends the thread, so the poll costs no issue slots to speak of.
 __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t *err) {
     uint32_t done = 0;
     uint64_t t0 = 0;
-    // one lane polls (the spin would otherwise take issue slots from the warps still computing); __syncwarp
-    // orders the others behind its acquire
-    if ((threadIdx.x & 31) == 0)
     for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
@@ -60,7 +59,7 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, uint32_t 
             const uint64_t now = tc_timer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 2000000000ull) {   // 2 s
-                atomicAdd(err, 1u);
+                if ((threadIdx.x & 31) == 0) atomicAdd(err, 1u);
                 break;
             }
         }
