@@ -3,7 +3,7 @@
 // G_I += sigma Z_J, G_J = sigma^T Z_I).  Reference: gae.py:71 + train_inductive.py:44-51.
 //
 // What differs from decoder_tc.cu (the TF32 form it supersedes; that kernel measured 359 us at the Pubmed shape with
-// the MUFU chain busy 23 % of the time -- everything else was un-overlapped latency; this one: 0.21 ms):
+// the MUFU chain busy 23 % of the time -- everything else was un-overlapped latency; this one: 235 us, MUFU pipe 42 % busy):
 //
 //  * Operands are split into TWO FP16 TERMS (hi = fp16(x), lo = fp16(x - hi): 11 + 11 significand bits, products
 //    exact in the fp32 accumulators, hi*hi + lo*hi + hi*lo as before -> the same ~2^-21 relative accuracy and the same
