@@ -96,6 +96,12 @@ SIGNATURES = {
     "gae_linear_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                    c_int32, c_void_p]),
+    "gae_gcn_layer_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "gae_gcn_layer_bwd_ws_bytes": (c_int64, [c_int64, c_int32, c_int32]),
+    "gae_gcn_layer_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "gae_dropout_fwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float,
                                     c_uint64, c_uint64, c_int32, c_void_p]),
     "gae_dropout_fwd_devrng_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float,

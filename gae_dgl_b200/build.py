@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgae_b200.so")
-SOURCES = ["api.cu", "spmm.cu", "spmm_stream.cu", "spmm_fused.cu", "linear.cu", "decoder.cu", "decoder_tc.cu", "decoder_tc16.cu", "misc.cu", "step.cu", "halo.cu"]
+SOURCES = ["api.cu", "spmm.cu", "spmm_stream.cu", "spmm_fused.cu", "linear.cu", "gcn_layer.cu", "decoder.cu", "decoder_tc.cu", "decoder_tc16.cu", "misc.cu", "step.cu", "halo.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tcgen05.cuh"), os.path.join(_HERE, "..", "include", "gae_b200.h")]
 
 NVCC_FLAGS = [

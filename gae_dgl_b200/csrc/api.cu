@@ -13,12 +13,12 @@ static std::atomic<int64_t> g_launches{0};
 // lane at 40 registers (48 warps/SM), 64-thread CTAs, plain caching, warp per row; decoder dense pass with
 // both GEMMs on the tensor cores (dec_mma = 1)
 // PER-THREAD: a sweep on one host thread never changes what another thread's calls launch
-static thread_local int32_t g_tuning[T_COUNT] = {0, 4, 64, 0, 1, 0, 2, 1, 2, 1, -1, 1, 4, 1, -1};
+static thread_local int32_t g_tuning[T_COUNT] = {0, 4, 64, 0, 1, 0, 2, 1, 2, 1, -1, 1, 4, 1, -1, 1};
 static const char *const g_tuning_names[T_COUNT] = {"spmm_variant", "spmm_unroll", "spmm_block",
                                                      "spmm_cache", "spmm_rows_per_warp", "dec_splits",
                                                      "spmm_stages", "spmm_bins", "dec_rows",
                                                      "spmm_seg_order", "spmm_fused", "dec_mma", "push_unroll",
-                                                     "push_stream_ld", "dec_tc"};
+                                                     "push_stream_ld", "dec_tc", "gcn_fused"};
 
 void set_error(const char *fmt, ...) {
     va_list ap;

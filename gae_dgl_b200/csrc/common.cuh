@@ -30,6 +30,7 @@ enum TuningIdx {
     T_DEC_TC,            // decoder dense pass, d <= 16: tcgen05 / TMEM symmetric-half kernels -- -1 = by size (default: the fp16-split
                          // pipelined form from 4096 rows), 2 = that form (decoder_tc16.cu) from 512 rows, 1 = TF32 form
                          // (decoder_tc.cu), 0 = mma.sync / SIMT forms
+    T_GCN_FUSED,         // gae_step_fwd_bwd_f32: 1 = layers with d_in, d_out <= 64 and no hub rows in ONE launch (gcn_layer.cu), 0 = SpMM + Linear
     T_COUNT
 };
 

@@ -110,12 +110,24 @@ extern "C" int gae_step_fwd_bwd_f32(const gae_step_desc_t *desc, int64_t n, cons
         const bool pre = l == 0 && desc->x_aggregated;       // X is A X already
         const float *y = pre ? X : sb.Y[l];
         const int64_t ldy = pre ? ldx : ld4(din);
+        float *out = (l == L - 1) ? Z_out : sb.H[l];
+        const int64_t ldo = (l == L - 1) ? ldz : ld4(dout);
+        // the whole layer in one launch where the aggregated row fits a warp's registers and no row needs the hub-segment
+        // plan (gcn_layer.cu); Y is kept only when the backward pass will read it
+        const bool fused = !pre && tuning(T_GCN_FUSED) != 0 && din <= 64 && dout <= 64 && (!plan || plan->n_long == 0) &&
+                           ldh % 4 == 0 && aligned16(h);
+        if (fused) {
+            rc = gae_gcn_layer_fwd_f32(rowptr, col, h, ldh, W[l], b[l], out, ldo, want_grad ? sb.Y[l] : nullptr, ld4(din), n, din, dout,
+                                       desc->acts[l], stream);
+            if (rc) return rc;
+            h = out;
+            ldh = ldo;
+            continue;
+        }
         if (!pre) {
             rc = gae_spmm_csr_f32(rowptr, col, nullptr, h, ldh, sb.Y[l], ld4(din), n, din, plan, sb.hub_ws, 0, stream);
             if (rc) return rc;
         }
-        float *out = (l == L - 1) ? Z_out : sb.H[l];
-        const int64_t ldo = (l == L - 1) ? ldz : ld4(dout);
         rc = gae_linear_fwd_f32(y, ldy, W[l], b[l], out, ldo, n, din, dout, desc->acts[l], stream);
         if (rc) return rc;
         h = out;

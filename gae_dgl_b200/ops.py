@@ -257,6 +257,55 @@ def linear_bwd(Y: torch.Tensor, W: torch.Tensor, H: torch.Tensor, dH: torch.Tens
     return dY, dW, db
 
 
+def gcn_layer_fwd(rowptr: torch.Tensor, col: torch.Tensor, Hin: torch.Tensor, W: torch.Tensor,
+                  b: Optional[torch.Tensor], act: int, want_y: bool = False):
+    """One GCN layer in one launch (gae.py:26-31): returns (act((A Hin) W^T + b), A Hin or None).
+    d_in, d_out <= 64 (gae_gcn_layer_fwd_f32)."""
+    _require_cuda(rowptr, "rowptr", torch.int64)
+    _require_cuda(col, "col", torch.int32)
+    Hin = as_rows(Hin, "Hin")
+    _require_cuda(W, "W")
+    W = W.contiguous()
+    n, d_in = Hin.shape
+    d_out = W.shape[0]
+    if W.shape[1] != d_in or rowptr.numel() - 1 != n:
+        raise GaeError("gcn_layer_fwd: shapes do not match")
+    H = alloc_rows(n, d_out, Hin.device)
+    Y = alloc_rows(n, d_in, Hin.device) if want_y else None
+    bb = None if b is None else b.contiguous()
+    rc = _lib.load().gae_gcn_layer_fwd_f32(_ptr(rowptr), _ptr(col), _ptr(Hin), _ld(Hin), _ptr(W), _ptr(bb), _ptr(H), _ld(H),
+                                           _ptr(Y), _ld(Y) if Y is not None else 0, n, d_in, d_out, act, _stream())
+    _lib.check(rc, "gae_gcn_layer_fwd_f32")
+    return H, Y
+
+
+def gcn_layer_bwd(rowptr_t: Optional[torch.Tensor], col_t: Optional[torch.Tensor], Y: torch.Tensor, W: torch.Tensor,
+                  H: torch.Tensor, dH: torch.Tensor, act: int, need_dhin: bool, plan_t: Optional[HubPlan] = None):
+    """Adjoint of gcn_layer_fwd (gae_gcn_layer_bwd_f32): returns (dHin or None, dW, db)."""
+    Y = as_rows(Y, "Y")
+    dH = as_rows(dH, "dH")
+    W = W.contiguous()
+    n, d_in = Y.shape
+    d_out = W.shape[0]
+    lib = _lib.load()
+    ws_bytes = lib.gae_gcn_layer_bwd_ws_bytes(n, d_in, d_out)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=Y.device)
+    dW = torch.empty((d_out, d_in), dtype=torch.float32, device=Y.device)
+    db = torch.empty((d_out,), dtype=torch.float32, device=Y.device)
+    dY = alloc_rows(n, d_in, Y.device) if need_dhin else None
+    dHin = alloc_rows(n, d_in, Y.device) if need_dhin else None
+    plan_ref, hub_ws = None, None
+    if need_dhin and plan_t is not None and (plan_t.n_seg > 0 or plan_t.bins is not None):
+        plan_ref = ctypes.byref(plan_t.struct)
+        hub_ws = plan_t.workspace(d_in, Y.device)
+    rc = lib.gae_gcn_layer_bwd_f32(_ptr(rowptr_t), _ptr(col_t), plan_ref, _ptr(hub_ws), _ptr(Y), _ld(Y), _ptr(W), _ptr(H), _ld(H),
+                                   _ptr(dH), _ld(dH), _ptr(dY), _ld(dY) if dY is not None else 0, _ptr(dHin),
+                                   _ld(dHin) if dHin is not None else 0, _ptr(dW), _ptr(db), _ptr(ws), ws_bytes, n, d_in, d_out,
+                                   act, _stream())
+    _lib.check(rc, "gae_gcn_layer_bwd_f32")
+    return dHin, dW, db
+
+
 def dropout_fwd(Z: torch.Tensor, p: float, mask: Optional[torch.Tensor] = None,
                 seed: int = 0, offset: int = 0, rng_state: Optional[torch.Tensor] = None
                 ) -> Tuple[torch.Tensor, torch.Tensor]:

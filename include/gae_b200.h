@@ -51,7 +51,8 @@ const char *gae_last_error_string(void);
  * "dec_splits" (0 = auto), "dec_rows" (2), "dec_tc" (-1: by size -- the tcgen05 / TMEM fp16-split pass
  * for d <= 16 from 4096 rows; 2 / 1: that pass / its TF32 predecessor from 512 rows; 0: never),
  * "dec_mma" (1: below that, dense pass as mma.sync TF32 MMAs for d <= 16; 0: SIMT), "push_unroll" (4),
- * "push_stream_ld" (1).  The knobs are PER HOST THREAD.
+ * "push_stream_ld" (1), "gcn_fused" (1: gae_step_fwd_bwd_f32 runs its layers through gae_gcn_layer_fwd_f32
+ * where it applies; 0: SpMM + Linear).  The knobs are PER HOST THREAD.
  * Results are independent of every knob up to fp32 summation order.
  * Unknown keys return GAE_ERR_INVALID_ARG.  gae_get_tuning returns the value or -1. */
 int gae_set_tuning(const char *key, int32_t value);
@@ -137,6 +138,27 @@ int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *W, const fl
                        int64_t ld_out, const float *dH, int64_t ld_dh, float *dYin,
                        int64_t ld_dyin, float *dW, float *db, void *ws, int64_t ws_bytes,
                        int64_t n, int32_t d_in, int32_t d_out, int32_t act, void *stream);
+
+/* ---- K1 + K3 in one launch: a whole GCN layer --------------------------------------------- */
+/* Replaces  g.update_all(gcn_msg, gcn_reduce); g.apply_nodes(func=self.apply_mod)   gae.py:26-31
+ * (SURVEY.md 8b `gae_gcn_layer_fwd/bwd_f32`):  Hout[n,d_out] = act((A Hin) W^T + b) without the round trip
+ * of Y = A Hin through HBM.  d_in, d_out <= 64; Hin (and Y) rows 16-byte aligned, row strides multiples of
+ * 4 floats >= d_in rounded up to 4 (else GAE_ERR_UNSUPPORTED: use gae_spmm_csr_f32 + gae_linear_fwd_f32).
+ * Y may be NULL (encode / evaluation); training passes it, dW = dPre^T Y needs the aggregated rows. */
+int gae_gcn_layer_fwd_f32(const int64_t *rowptr, const int32_t *col, const float *Hin, int64_t ldh,
+                          const float *W, const float *b, float *Hout, int64_t ldo, float *Y,
+                          int64_t ldy, int64_t n, int32_t d_in, int32_t d_out, int32_t act,
+                          void *stream);
+/* Adjoint of the layer in one call: dW, db, and -- unless dHin is NULL (first layer, gae.py:50) --
+ * dHin = A^T (dPre W) over CSR(A^T) (plan_t / hub_ws_t as for gae_spmm_csr_f32, may be NULL).
+ * dY: scratch rows [n, ld_dy]; ws: gae_gcn_layer_bwd_ws_bytes() bytes. */
+int64_t gae_gcn_layer_bwd_ws_bytes(int64_t n, int32_t d_in, int32_t d_out);
+int gae_gcn_layer_bwd_f32(const int64_t *rowptr_t, const int32_t *col_t, const gae_hub_plan_t *plan_t,
+                          float *hub_ws_t, const float *Y, int64_t ldy, const float *W,
+                          const float *Hout, int64_t ldo, const float *dHout, int64_t ld_dh, float *dY,
+                          int64_t ld_dy, float *dHin, int64_t ld_dhin, float *dW, float *db, void *ws,
+                          int64_t ws_bytes, int64_t n, int32_t d_in, int32_t d_out, int32_t act,
+                          void *stream);
 
 /* ---- K4: dropout (always on in the reference decoder) ------------------------------------ */
 /* Replaces  z = F.dropout(z, self.dropout)   gae.py:70  (training=True regardless of mode).

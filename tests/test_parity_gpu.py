@@ -238,6 +238,47 @@ def test_linear_fwd_bwd_parity(cuda, n, d_in, d_out, act):
     assert rel_err(bc.grad, br.grad) < TOL
 
 
+@pytest.mark.parametrize("n,e,hub,d_in,d_out,act", [(3000, 9000, None, 39, 32, 1), (600, 2500, 300, 32, 16, 0),
+                                                      (2000, 30000, None, 64, 64, 1), (130, 400, None, 5, 7, 1),
+                                                      (900, 4000, 2000, 16, 33, 1)])
+def test_gcn_layer_single_launch_parity(cuda, n, e, hub, d_in, d_out, act):
+    """gae_gcn_layer_fwd/bwd_f32: the whole layer of gae.py:26-31 in one launch vs fp64 autograd over
+    the dense adjacency (duplicate edges, empty rows, a hub row), and its Y output vs the SpMM kernel."""
+    src, dst = random_graph(n, e, seed=n + d_in, hub=hub)
+    src = torch.cat([src, src[:15]])
+    dst = torch.cat([dst, dst[:15]])
+    rowptr, col = O.coo_to_csr(src, dst, n)
+    rt, ct = O.csr_transpose(rowptr, col)
+    g = torch.Generator().manual_seed(e)
+    Hin = torch.randn(n, d_in, generator=g)
+    W = torch.randn(d_out, d_in, generator=g) / d_in ** 0.5
+    b = torch.randn(d_out, generator=g)
+    dH = torch.randn(n, d_out, generator=g)
+    A = O.dense_adj(src, dst, n, torch.float64)
+    Hr, Wr, br = (t.double().requires_grad_(True) for t in (Hin, W, b))
+    Yr = A @ Hr
+    pre = Yr @ Wr.t() + br
+    out_r = torch.relu(pre) if act else pre
+    out_r.backward(dH.double())
+    rp, cl = to_dev(rowptr, col, cuda)
+    H, Y = ops.gcn_layer_fwd(rp, cl, Hin.to(cuda), W.to(cuda), b.to(cuda), act, want_y=True)
+    assert rel_err(H, out_r) < TOL
+    assert rel_err(Y, Yr) < TOL
+    H2, none = ops.gcn_layer_fwd(rp, cl, Hin.to(cuda), W.to(cuda), b.to(cuda), act, want_y=False)
+    assert none is None and torch.equal(H2, H)                          # Y is a side output only
+    assert rel_err(Y, ops.spmm(rp, cl, Hin.to(cuda))) < 1e-6
+    rtd, ctd = to_dev(rt, ct, cuda)
+    dHin, dW, db = ops.gcn_layer_bwd(rtd, ctd, Y, W.to(cuda), H, dH.to(cuda), act, need_dhin=True)
+    assert rel_err(dHin, Hr.grad) < TOL
+    assert rel_err(dW, Wr.grad) < TOL
+    assert rel_err(db, br.grad) < TOL
+    none, dW1, db1 = ops.gcn_layer_bwd(None, None, Y, W.to(cuda), H, dH.to(cuda), act, need_dhin=False)
+    assert none is None and torch.equal(dW1, dW) and torch.equal(db1, db)
+    # widths beyond the kernel's reach are refused, not mangled
+    with pytest.raises(G.GaeError):
+        ops.gcn_layer_fwd(rp, cl, torch.randn(n, 65, device=cuda), torch.randn(8, 65, device=cuda), None, 0)
+
+
 def test_dropout_mask_injection_and_philox(cuda):
     Z = torch.randn(1000, 16, device=cuda)
     mask = (torch.rand(1000, 16) >= 0.1)

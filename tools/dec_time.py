@@ -14,7 +14,13 @@ from gae_dgl_b200 import _lib, ops, synthetic  # noqa: E402
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 name = sys.argv[1]
-g, X = synthetic.planetoid_like(name, seed=0)
+if name.startswith("n") and name[1:].isdigit():          # "n6000": a random graph with that many vertices, 5 edges per vertex
+    import gae_dgl_b200 as G
+    nn = int(name[1:])
+    gen = torch.Generator().manual_seed(nn)
+    g = G.DGLGraph((torch.randint(0, nn, (5 * nn,), generator=gen).numpy(), torch.randint(0, nn, (5 * nn,), generator=gen).numpy(), nn))
+else:
+    g, X = synthetic.planetoid_like(name, seed=0)
 g.to(dev)
 c, t = g.csr(), g.csr_t()
 Zd = torch.randn(g.number_of_nodes(), 16, device=dev) * 0.3
