@@ -334,7 +334,7 @@ def cuda_time_ms(fn, steps, stream):
 def decoder_roofline(dev, g, d=16, iters=20):
     """Roofline of the dominant kernel of the small-graph train steps: the fused decoder (dense pass over the pairs
     + partial-slot reduce + finalize + loss reduce), timed ALONE with CUDA events on its launching stream.
-    From 4096 rows (d <= 16) the dense pass is the tcgen05 symmetric-half kernel: it evaluates N^2 / 2 pairs, so the
+    From 5632 rows (d <= 16) the dense pass is the tcgen05 symmetric-half kernel: it evaluates N^2 / 2 pairs, so the
     algorithmic work per launch is 3 N^2 d flop (S over the upper triangle: N^2 d; G_I and G_J:
     N^2 d each) and N^2 MUFU ops (ex2 + rcp per evaluated pair; lg2 folded 32:1); below that the mma.sync / SIMT forms
     walk all N^2 pairs: 4 N^2 d flop, 2 N^2 MUFU ops.  `bound` is "tensor": peak = the MEASURED bf16 rate (fp16 operands
@@ -356,7 +356,7 @@ def decoder_roofline(dev, g, d=16, iters=20):
         fn()
     torch.cuda.synchronize()
     ms = cuda_time_ms(fn, iters, st) / iters
-    tc = d <= 16 and n >= 4096                      # DEC_TC_AUTO_ROWS (csrc/decoder.cu)
+    tc = d <= 16 and n >= 5632                      # DEC_TC_AUTO_ROWS (csrc/decoder.cu)
     flops = (3.0 if tc else 4.0) * n * n * d
     mufu = (1.0 if tc else 2.0) * n * n
     pk = {}

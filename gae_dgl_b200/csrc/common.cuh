@@ -28,7 +28,7 @@ enum TuningIdx {
     T_PUSH_UNROLL,       // halo push kernel: row steps in flight per lane group (4 or 8; registers 55 / 106)
     T_PUSH_STREAM_LD,    // halo push kernel: 1 = read the local rows with evict-first loads (ld.global.cs)
     T_DEC_TC,            // decoder dense pass, d <= 16: tcgen05 / TMEM symmetric-half kernels -- -1 = by size (default: the fp16-split
-                         // pipelined form from 4096 rows), 2 = that form (decoder_tc16.cu) from 512 rows, 1 = TF32 form
+                         // pipelined form from 5632 rows), 2 = that form (decoder_tc16.cu) from 512 rows, 1 = TF32 form
                          // (decoder_tc.cu), 0 = mma.sync / SIMT forms
     T_GCN_FUSED,         // gae_step_fwd_bwd_f32: 1 = layers with d_in, d_out <= 64 and no hub rows in ONE launch (gcn_layer.cu), 0 = SpMM + Linear
     T_COUNT

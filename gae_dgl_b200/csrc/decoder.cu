@@ -43,8 +43,9 @@ int dec_tc16_splits(int64_t n);
 cudaError_t dec_tc16_launch(const float *Zd, int64_t ldz, int64_t n, int d, int splits, float *dz_part, float *dzT_part,
                             double *loss_part, uint32_t *err, cudaStream_t st);
 constexpr int64_t DEC_TC_MIN_ROWS = 512;      // an explicit dec_tc = 1 / 2 applies from here
-constexpr int64_t DEC_TC_AUTO_ROWS = 4096;    // dec_tc = -1 (default): tcgen05 form from here, mma.sync form below -- a CTA's TMEM / barrier
-                                              // set-up and drain cost about two tiles (measured: Cora shape, 22 x 22 tiles, 42 us vs 32 us)
+constexpr int64_t DEC_TC_AUTO_ROWS = 5632;    // dec_tc = -1 (default): tcgen05 form from here (44 x 44 tiles), mma.sync form below -- a CTA's
+                                              // TMEM / barrier set-up and drain cost about two tiles and the form needs three more small launches
+                                              // (measured, whole decoder: 4096 rows 49 vs 40 us, 6000 rows 65 vs 69, 8192 rows 90 vs 106)
 
 static bool dec_config(int64_t n, int32_t d, DecConfig *c) {
     if (d <= 16) { c->D = 16; c->R = tuning(T_DEC_ROWS) == 1 ? 1 : 2; }

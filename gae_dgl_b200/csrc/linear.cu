@@ -138,6 +138,228 @@ static cudaError_t launch_gemm_bm(const GemmArgs &g, int splits, cudaStream_t st
     return cudaGetLastError();
 }
 
+// ---- fast paths for the two products that read the [n, d_in] activation matrix (round 2) ----------------------------
+// At the Pubmed shape (n = 19 717, d_in = 500, d_out = 32) the generic kernel above took 88 us for the forward product
+// and 88 + 13 + 13 us for dW / db -- a third of the train step once the decoder had shrunk -- at 0.45 TB/s and 7 TFLOP/s:
+// scalar global loads, 8 scalar LDS per 8 FMAs.  These two kernels keep the FP32 FFMA arithmetic (nn.Linear parity)
+// but move 128-bit everywhere: float4 global loads along the contiguous dimension, k-major shared tiles read back as
+// one LDS.128 per operand per k for a 4 x TN register tile (2 LDS per 16 FMAs), an XOR swizzle on the transposed store
+// of the activation tile (conflict-free both ways).  Requirements (else the generic kernel runs): 16-byte aligned
+// rows, row strides multiples of 4 floats.
+
+constexpr int FBM = 64, FBK = 32, F_THREADS = 128;
+
+// H[M, N] = act(A[M, K] W[N, K]^T + b), A rows K-contiguous (lda), W rows K-contiguous (stride K).  BN = 16 / 32 / 64.
+template <int BN>
+__global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W,
+                                                                   const float *__restrict__ bias, float *__restrict__ C, int64_t ldc,
+                                                                   int64_t M, int N, int K, int act) {
+    constexpr int TN = BN / 8;                          // 2 / 4 / 8 output columns per thread, 4 rows
+    __shared__ __align__(16) float As[FBK][FBM];        // [k][row], float4 groups of 4 rows XOR-swizzled by (k / 4) % 8
+    __shared__ __align__(16) float Bs[FBK][BN];         // [k][n]
+    const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+    const int64_t m0 = (int64_t)blockIdx.x * FBM;
+    const int n0 = blockIdx.y * BN;
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    constexpr int NB = BN * FBK / F_THREADS;            // W elements per thread per tile
+    float4 ra[4];
+    float rb[NB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + F_THREADS * j, row = f >> 3, k = k0 + 4 * (f & 7);
+            const int64_t m = m0 + row;
+            float4 v = f4_zero();
+            if (m < M) {
+                const float *p = A + m * lda + k;
+                if (k + 3 < K) v = __ldg(reinterpret_cast<const float4 *>(p));
+                else {
+                    if (k < K) v.x = __ldg(p);
+                    if (k + 1 < K) v.y = __ldg(p + 1);
+                    if (k + 2 < K) v.z = __ldg(p + 2);
+                }
+            }
+            ra[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int f = tid + F_THREADS * j, n = f % BN, k = k0 + f / BN;
+            rb[j] = (n0 + n < N && k < K) ? __ldg(W + (int64_t)(n0 + n) * K + k) : 0.f;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + F_THREADS * j, row = f >> 3, kq = f & 7;
+            const int col = 4 * ((row >> 2) ^ kq) + (row & 3);
+            As[4 * kq + 0][col] = ra[j].x;
+            As[4 * kq + 1][col] = ra[j].y;
+            As[4 * kq + 2][col] = ra[j].z;
+            As[4 * kq + 3][col] = ra[j].w;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int f = tid + F_THREADS * j;
+            Bs[f / BN][f % BN] = rb[j];
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += FBK) {
+        stash();
+        __syncthreads();
+        if (k0 + FBK < K) fetch(k0 + FBK);
+#pragma unroll
+        for (int kk = 0; kk < FBK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[kk][4 * (ty ^ ((kk >> 2) & 7))]);
+            float b[TN];
+            if (TN == 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 2]);
+                b[0] = t.x; b[1] = t.y;
+            } else {
+#pragma unroll
+                for (int j4 = 0; j4 < TN / 4; ++j4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN + 4 * j4]);
+                    b[4 * j4] = t.x; b[4 * j4 + 1] = t.y; b[4 * j4 + 2] = t.z; b[4 * j4 + 3] = t.w;
+                }
+            }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + 4 * ty + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += __ldg(bias + n);
+            if (act == GAE_ACT_RELU) v = fmaxf(v, 0.f);
+            C[m * ldc + n] = v;
+        }
+    }
+}
+
+// Partial dW and db over one chunk of rows:  part_w[z][o][c] = sum_{rows of chunk z} dPre[row][o] Y[row][c],
+// part_b[z][o] = sum dPre[row][o], dPre = dH (.) (H > 0) when H is given.  Both operands are read row by row with the
+// contracted index (the row) outermost, so the shared tiles are filled without a transpose.  BM = 32 / 64 (d_out).
+template <int BM>
+__global__ void __launch_bounds__(F_THREADS) linear_dw_kernel(const float *__restrict__ dH, int64_t ld_dh, const float *__restrict__ H, int64_t ld_h,
+                                                               const float *__restrict__ Y, int64_t ldy, float *__restrict__ part_w,
+                                                               float *__restrict__ part_b, int64_t n, int d_in, int d_out, int64_t chunk) {
+    constexpr int BN = 64, TM = BM / 8;                 // thread tile TM x 4
+    __shared__ __align__(16) float As[FBK][BM];         // [row][o]
+    __shared__ __align__(16) float Bs[FBK][BN];         // [row][c]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int c0 = blockIdx.x * BN;
+    const int64_t r_begin = (int64_t)blockIdx.y * chunk, r_end = min(n, r_begin + chunk);
+    float acc[TM][4];
+    float bsum[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        bsum[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    constexpr int NA = FBK * BM / 4 / F_THREADS;        // float4 per thread per tile: 2 (BM 32) / 4 (BM 64)
+    constexpr int NBQ = FBK * BN / 4 / F_THREADS;       // 4
+    float4 ra[NA], rb[NBQ];
+    auto fetch = [&](int64_t r0) {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const int f = tid + F_THREADS * j, rr = f / (BM / 4), o = 4 * (f % (BM / 4));
+            const int64_t row = r0 + rr;
+            float4 v = f4_zero();
+            if (row < r_end && o < d_out) {
+                v = __ldg(reinterpret_cast<const float4 *>(dH + row * ld_dh + o));       // ld_dh >= d_out rounded up to 4
+                if (H) {
+                    const float4 h = __ldg(reinterpret_cast<const float4 *>(H + row * ld_h + o));
+                    if (!(h.x > 0.f)) v.x = 0.f;
+                    if (!(h.y > 0.f)) v.y = 0.f;
+                    if (!(h.z > 0.f)) v.z = 0.f;
+                    if (!(h.w > 0.f)) v.w = 0.f;
+                }
+                if (o + 1 >= d_out) v.y = 0.f;
+                if (o + 2 >= d_out) v.z = 0.f;
+                if (o + 3 >= d_out) v.w = 0.f;
+            }
+            ra[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < NBQ; ++j) {
+            const int f = tid + F_THREADS * j, rr = f / (BN / 4), c = c0 + 4 * (f % (BN / 4));
+            const int64_t row = r0 + rr;
+            float4 v = f4_zero();
+            if (row < r_end && c < d_in) {
+                v = __ldg(reinterpret_cast<const float4 *>(Y + row * ldy + c));          // ldy >= d_in rounded up to 4
+                if (c + 1 >= d_in) v.y = 0.f;
+                if (c + 2 >= d_in) v.z = 0.f;
+                if (c + 3 >= d_in) v.w = 0.f;
+            }
+            rb[j] = v;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const int f = tid + F_THREADS * j;
+            *reinterpret_cast<float4 *>(&As[f / (BM / 4)][4 * (f % (BM / 4))]) = ra[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NBQ; ++j) {
+            const int f = tid + F_THREADS * j;
+            *reinterpret_cast<float4 *>(&Bs[f / (BN / 4)][4 * (f % (BN / 4))]) = rb[j];
+        }
+    };
+    if (r_begin < r_end) fetch(r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += FBK) {
+        stash();
+        __syncthreads();
+        if (r0 + FBK < r_end) fetch(r0 + FBK);
+#pragma unroll
+        for (int kk = 0; kk < FBK; ++kk) {
+            float a[TM];
+#pragma unroll
+            for (int i4 = 0; i4 < TM / 4; ++i4) {
+                const float4 t = *reinterpret_cast<const float4 *>(&As[kk][ty * TM + 4 * i4]);
+                a[4 * i4] = t.x; a[4 * i4 + 1] = t.y; a[4 * i4 + 2] = t.z; a[4 * i4 + 3] = t.w;
+            }
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][4 * tx]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+                bsum[i] += a[i];
+            }
+        }
+        __syncthreads();
+    }
+    float *pw = part_w + (int64_t)blockIdx.y * d_out * d_in;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int o = ty * TM + i;
+        if (o >= d_out) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * tx + j;
+            if (c < d_in) pw[(int64_t)o * d_in + c] = acc[i][j];
+        }
+        if (blockIdx.x == 0 && tx == 0) part_b[(int64_t)blockIdx.y * d_out + o] = bsum[i];
+    }
+}
+
 template <bool A_KC, bool B_KC>
 static cudaError_t launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
     if (g.M == 0 || g.N == 0) return cudaSuccess;
@@ -147,14 +369,32 @@ static cudaError_t launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
     return launch_gemm_bm<64, A_KC, B_KC>(g, splits, st);
 }
 
-// out[i] = sum_z part[z*stride + i] in fixed z order (deterministic split-K reduce)
-__global__ void split_reduce_kernel(const float *__restrict__ part, int64_t stride, int splits,
-                                    float *__restrict__ out, int64_t count) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+// out[i] = sum_z part[z*stride + i], deterministic split-K reduce.  A block covers 32 outputs; its 8 warps take every
+// 8th partial each (lane = output: coalesced), then meet in shared memory in warp order.  (One thread per output
+// walking all ~100 partials took 13 us per call at the Pubmed shape -- four calls per step, all of it load latency.)
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float *__restrict__ part, int64_t stride, int splits,
+                                                          float *__restrict__ out, int64_t count) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
-    out[i] = s;
+    if (i < count) {
+        int z = warp;
+        for (; z + 24 < splits; z += 32) {              // four loads in flight
+            const float a = part[(int64_t)z * stride + i], b = part[(int64_t)(z + 8) * stride + i];
+            const float c = part[(int64_t)(z + 16) * stride + i], d = part[(int64_t)(z + 24) * stride + i];
+            s += a; s += b; s += c; s += d;
+        }
+        for (; z < splits; z += 8) s += part[(int64_t)z * stride + i];
+    }
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < count) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += red[w][lane];
+        out[i] = t;
+    }
 }
 
 // partial column sums of dPre = dH * (H > 0): part[z, j] over row chunk z
@@ -212,12 +452,21 @@ extern "C" int gae_linear_fwd_f32(const float *Yin, int64_t ld_in, const float *
     GAE_CHECK_ARG(Yin && W && H, "null pointer");
     GAE_CHECK_ARG(ld_in >= d_in && ld_out >= d_out, "leading dimension too small");
     GAE_CHECK_ARG(act == GAE_ACT_IDENTITY || act == GAE_ACT_RELU, "unknown activation");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aligned16(Yin) && ld_in % 4 == 0 && ld_in >= (d_in + 3) / 4 * 4 && d_out <= 64) {      // 128-bit path
+        dim3 grid((unsigned)cdiv(n, FBM), 1);
+        if (d_out <= 16) linear_fwd_tn_kernel<16><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        else if (d_out <= 32) linear_fwd_tn_kernel<32><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        else linear_fwd_tn_kernel<64><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        GAE_LAUNCH_CHECK();
+        return GAE_OK;
+    }
     GemmArgs g{};
     g.A = Yin; g.a_rs = ld_in; g.a_cs = 1;
     g.B = W; g.b_rs = 1; g.b_cs = d_in;   // B(k, j) = W[j, k]
     g.C = H; g.ldc = ld_out; g.bias = b;
     g.M = n; g.N = d_out; g.K = d_in; g.k_chunk = d_in; g.act = act;
-    GAE_CUDA((launch_gemm<true, true>(g, 1, (cudaStream_t)stream)));
+    GAE_CUDA((launch_gemm<true, true>(g, 1, st)));
     return GAE_OK;
 }
 
@@ -225,7 +474,8 @@ extern "C" int64_t gae_linear_bwd_ws_bytes(int64_t n, int32_t d_in, int32_t d_ou
     if (n <= 0 || d_in <= 0 || d_out <= 0) return 0;
     int splits; int64_t chunk;
     bwd_split_config(n, d_in, d_out, &splits, &chunk);
-    const int64_t db_blocks = cdiv(n, db_rows_per_block(n));
+    int64_t db_blocks = cdiv(n, db_rows_per_block(n));
+    if (db_blocks < splits) db_blocks = splits;          // the 128-bit dW kernel writes one db partial per row chunk
     return (int64_t)sizeof(float) * ((int64_t)splits * d_out * d_in + db_blocks * d_out);
 }
 
@@ -253,6 +503,21 @@ extern "C" int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *
     float *part_w = (float *)ws;
     float *part_b = part_w + (int64_t)splits * d_out * d_in;
 
+    const int64_t do4 = (d_out + 3) / 4 * 4, di4 = (d_in + 3) / 4 * 4;
+    const bool fast = d_out <= 64 && aligned16(dH) && ld_dh % 4 == 0 && ld_dh >= do4 && aligned16(Yin) && ld_in % 4 == 0 && ld_in >= di4 &&
+                      (!mask || (aligned16(mask) && ld_out % 4 == 0 && ld_out >= do4));
+    if (fast) {
+        // dW and db partials per row chunk in one launch (128-bit loads, no transpose), then the two ordered reductions
+        dim3 grid((unsigned)cdiv(d_in, 64), (unsigned)splits);
+        if (d_out <= 32) linear_dw_kernel<32><<<grid, F_THREADS, 0, st>>>(dH, ld_dh, mask, ld_out, Yin, ld_in, part_w, part_b, n, d_in, d_out, chunk);
+        else linear_dw_kernel<64><<<grid, F_THREADS, 0, st>>>(dH, ld_dh, mask, ld_out, Yin, ld_in, part_w, part_b, n, d_in, d_out, chunk);
+        GAE_LAUNCH_CHECK();
+        const int64_t cnt = (int64_t)d_out * d_in;
+        split_reduce_kernel<<<(unsigned)cdiv(cnt, 32), 256, 0, st>>>(part_w, cnt, splits, dW, cnt);
+        GAE_LAUNCH_CHECK();
+        split_reduce_kernel<<<(unsigned)cdiv(d_out, 32), 256, 0, st>>>(part_b, d_out, splits, db, d_out);
+        GAE_LAUNCH_CHECK();
+    } else {
     // dW[j,k] = sum_n dPre[n,j] Yin[n,k]:  A(m=j,k=n) = dH[n*ld + j], B(k=n, n=k) = Yin[n*ld + k]
     {
         GemmArgs g{};
@@ -263,7 +528,7 @@ extern "C" int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *
         g.M = d_out; g.N = d_in; g.K = n; g.k_chunk = chunk; g.act = GAE_ACT_IDENTITY;
         GAE_CUDA((launch_gemm<false, false>(g, splits, st)));
         const int64_t cnt = (int64_t)d_out * d_in;
-        split_reduce_kernel<<<(unsigned)cdiv(cnt, 256), 256, 0, st>>>(part_w, cnt, splits, dW, cnt);
+        split_reduce_kernel<<<(unsigned)cdiv(cnt, 32), 256, 0, st>>>(part_w, cnt, splits, dW, cnt);
         GAE_LAUNCH_CHECK();
     }
     // db[j] = sum_n dPre[n,j]
@@ -273,8 +538,9 @@ extern "C" int gae_linear_bwd_f32(const float *Yin, int64_t ld_in, const float *
         colsum_masked_kernel<<<(unsigned)blocks, dim3(32, 8), 0, st>>>(dH, ld_dh, mask, ld_out, mask != nullptr, n,
                                                                        d_out, rows_per_block, part_b);
         GAE_LAUNCH_CHECK();
-        split_reduce_kernel<<<(unsigned)cdiv(d_out, 256), 256, 0, st>>>(part_b, d_out, (int)blocks, db, d_out);
+        split_reduce_kernel<<<(unsigned)cdiv(d_out, 32), 256, 0, st>>>(part_b, d_out, (int)blocks, db, d_out);
         GAE_LAUNCH_CHECK();
+    }
     }
     // dYin[n,k] = sum_j dPre[n,j] W[j,k]
     if (dYin) {

@@ -49,7 +49,7 @@ const char *gae_last_error_string(void);
  * "spmm_rows_per_warp" (1), "spmm_stages" (2), "spmm_bins" (1), "spmm_seg_order" (1), "spmm_fused"
  * (-1 = automatic; 1 / 0: single-launch form of the binned forward on / off),
  * "dec_splits" (0 = auto), "dec_rows" (2), "dec_tc" (-1: by size -- the tcgen05 / TMEM fp16-split pass
- * for d <= 16 from 4096 rows; 2 / 1: that pass / its TF32 predecessor from 512 rows; 0: never),
+ * for d <= 16 from 5632 rows; 2 / 1: that pass / its TF32 predecessor from 512 rows; 0: never),
  * "dec_mma" (1: below that, dense pass as mma.sync TF32 MMAs for d <= 16; 0: SIMT), "push_unroll" (4),
  * "push_stream_ld" (1), "gcn_fused" (1: gae_step_fwd_bwd_f32 runs its layers through gae_gcn_layer_fwd_f32
  * where it applies; 0: SpMM + Linear).  The knobs are PER HOST THREAD.
