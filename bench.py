@@ -624,16 +624,22 @@ def run_ours(args):
     alg_bytes = spmm_algorithmic_bytes(local_edges, local_rows, D_FEAT)
     # the fwd event pair brackets the row kernel + hub-segment kernel + hub reduce (+ exchange at N>1)
     achieved = alg_bytes / (statistics.mean(fwd_ms) * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_bwd = None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tpath) and world == 1 and (scale, total_edges) == (22, 100_000_000):
         # an ncu capture of the single-GPU C4 launch (profiles/): means nothing for any other workload
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_bwd = tj.get("dram_bytes_per_launch"), tj.get("bwd_dram_bytes_per_launch")
+    # SURVEY 8(d) secondary model: every byte touched once (col ids, row pointers, X read once, Y written once)
+    compulsory = 4 * local_edges + 8 * (local_rows + 1) + 2 * 4 * D_FEAT * local_rows
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "spmm_vec_kernel (fwd: rows + hub segments + hub reduce)",
+                "traffic": traffic, "kernel": "spmm_fused_kernel (fwd: every row class + hub segments in one launch) + spmm_hub_reduce_kernel",
                 "algorithmic_bytes": alg_bytes, "fwd_ms": statistics.mean(fwd_ms), "bwd_ms": statistics.mean(bwd_ms),
-                "peak_source": peak_src}
+                "peak_source": peak_src, "compulsory_bytes": compulsory,
+                "frac_compulsory": compulsory / (statistics.mean(fwd_ms) * 1e-3) / 1e9 / peak}
+    if traffic_bwd:
+        roofline["traffic_bwd"] = traffic_bwd
     if traffic and world == 1:
         # the DRAM-side view of the same launch: bytes that actually crossed HBM (ncu capture of this
         # workload, profiles/spmm_traffic.json) over the live forward time; `frac` above can exceed 1

@@ -148,16 +148,20 @@ static cudaError_t launch_gemm_bm(const GemmArgs &g, int splits, cudaStream_t st
 // rows, row strides multiples of 4 floats.
 
 constexpr int FBM = 64, FBK = 32, F_THREADS = 128;
+constexpr int FW_THREADS = 256;                        // forward kernel: two groups of 128 threads split each k tile between them
 
 // H[M, N] = act(A[M, K] W[N, K]^T + b), A rows K-contiguous (lda), W rows K-contiguous (stride K).  BN = 16 / 32 / 64.
 template <int BN>
-__global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W,
-                                                                   const float *__restrict__ bias, float *__restrict__ C, int64_t ldc,
-                                                                   int64_t M, int N, int K, int act) {
+__global__ void __launch_bounds__(FW_THREADS) linear_fwd_tn_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W,
+                                                                    const float *__restrict__ bias, float *__restrict__ C, int64_t ldc,
+                                                                    int64_t M, int N, int K, int act) {
     constexpr int TN = BN / 8;                          // 2 / 4 / 8 output columns per thread, 4 rows
     __shared__ __align__(16) float As[FBK][FBM];        // [k][row], float4 groups of 4 rows XOR-swizzled by (k / 4) % 8
-    __shared__ __align__(16) float Bs[FBK][BN];         // [k][n]
-    const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+    __shared__ __align__(16) float Bs[FBK][BN];         // [k][n], float4 groups of 4 columns XOR-swizzled by (k / 4) % (BN / 4)
+    __shared__ float red[F_THREADS][4 * TN + 1];        // second group's accumulators on their way to the first
+    // Two groups of 128 threads own the same 64 x BN output tile and take k 0..15 / 16..31 of every k tile: twice the
+    // warps per tile to cover the latency of the next tile's global loads (the grid is only ~2 CTAs per SM at n = 2e4).
+    const int tid = threadIdx.x, grp = tid >> 7, t2 = tid & 127, ty = t2 >> 3, tx = t2 & 7;
     const int64_t m0 = (int64_t)blockIdx.x * FBM;
     const int n0 = blockIdx.y * BN;
     float acc[4][TN];
@@ -165,13 +169,13 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    constexpr int NB = BN * FBK / F_THREADS;            // W elements per thread per tile
-    float4 ra[4];
+    constexpr int NB = BN * FBK / FW_THREADS;           // W elements per thread per tile
+    float4 ra[2];
     float rb[NB];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int f = tid + F_THREADS * j, row = f >> 3, k = k0 + 4 * (f & 7);
+        for (int j = 0; j < 2; ++j) {
+            const int f = tid + FW_THREADS * j, row = f >> 3, k = k0 + 4 * (f & 7);
             const int64_t m = m0 + row;
             float4 v = f4_zero();
             if (m < M) {
@@ -186,15 +190,15 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
             ra[j] = v;
         }
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int f = tid + F_THREADS * j, n = f % BN, k = k0 + f / BN;
+        for (int j = 0; j < NB; ++j) {              // a warp reads 32 consecutive k of one W row: one line per load
+            const int f = tid + FW_THREADS * j, k = k0 + (f & 31), n = f >> 5;
             rb[j] = (n0 + n < N && k < K) ? __ldg(W + (int64_t)(n0 + n) * K + k) : 0.f;
         }
     };
     auto stash = [&]() {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int f = tid + F_THREADS * j, row = f >> 3, kq = f & 7;
+        for (int j = 0; j < 2; ++j) {
+            const int f = tid + FW_THREADS * j, row = f >> 3, kq = f & 7;
             const int col = 4 * ((row >> 2) ^ kq) + (row & 3);
             As[4 * kq + 0][col] = ra[j].x;
             As[4 * kq + 1][col] = ra[j].y;
@@ -203,8 +207,8 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            const int f = tid + F_THREADS * j;
-            Bs[f / BN][f % BN] = rb[j];
+            const int f = tid + FW_THREADS * j, kk = f & 31, n = f >> 5;
+            Bs[kk][4 * ((n >> 2) ^ ((kk >> 2) & (BN / 4 - 1))) + (n & 3)] = rb[j];
         }
     };
     fetch(0);
@@ -213,16 +217,18 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
         __syncthreads();
         if (k0 + FBK < K) fetch(k0 + FBK);
 #pragma unroll
-        for (int kk = 0; kk < FBK; ++kk) {
+        for (int kh = 0; kh < FBK / 2; ++kh) {
+            const int kk = kh + (FBK / 2) * grp;
             const float4 a = *reinterpret_cast<const float4 *>(&As[kk][4 * (ty ^ ((kk >> 2) & 7))]);
             float b[TN];
-            if (TN == 2) {
-                const float2 t = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 2]);
+            constexpr int SW = BN / 4 - 1;
+            if (TN == 2) {                              // columns 2 tx, 2 tx + 1: half of float4 group tx / 2
+                const float2 t = *reinterpret_cast<const float2 *>(&Bs[kk][4 * ((tx >> 1) ^ ((kk >> 2) & SW)) + 2 * (tx & 1)]);
                 b[0] = t.x; b[1] = t.y;
             } else {
 #pragma unroll
                 for (int j4 = 0; j4 < TN / 4; ++j4) {
-                    const float4 t = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN + 4 * j4]);
+                    const float4 t = *reinterpret_cast<const float4 *>(&Bs[kk][4 * ((tx * (TN / 4) + j4) ^ ((kk >> 2) & SW))]);
                     b[4 * j4] = t.x; b[4 * j4 + 1] = t.y; b[4 * j4 + 2] = t.z; b[4 * j4 + 3] = t.w;
                 }
             }
@@ -234,6 +240,14 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
         }
         __syncthreads();
     }
+    if (grp == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) red[t2][i * TN + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (grp == 1) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t m = m0 + 4 * ty + i;
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(F_THREADS) linear_fwd_tn_kernel(const float *_
         for (int j = 0; j < TN; ++j) {
             const int n = n0 + tx * TN + j;
             if (n >= N) continue;
-            float v = acc[i][j];
+            float v = acc[i][j] + red[t2][i * TN + j];
             if (bias) v += __ldg(bias + n);
             if (act == GAE_ACT_RELU) v = fmaxf(v, 0.f);
             C[m * ldc + n] = v;
@@ -430,7 +444,7 @@ static inline int64_t db_rows_per_block(int64_t n) { return n / 2048 > 256 ? n /
 static void bwd_split_config(int64_t n, int32_t d_in, int32_t d_out, int *splits, int64_t *k_chunk) {
     // enough CTAs to fill 148 SMs a few times, chunks a multiple of BK, at most 1024 splits
     const int64_t tiles = cdiv(d_out, d_out <= 32 ? 32 : 64) * cdiv(d_in, d_in <= 16 ? 16 : d_in <= 32 ? 32 : 64);
-    int64_t want = cdiv(148 * 6, tiles);
+    int64_t want = cdiv(148 * 6, tiles);          // (148 * 3: the dW kernel of the Pubmed input layer went from ~40 to 57 us -- it needs the CTAs)
     int64_t chunk = cdiv(cdiv(n, want), BK) * BK;
     if (chunk < 64) chunk = 64;
     int64_t s = cdiv(n, chunk);
@@ -455,9 +469,9 @@ extern "C" int gae_linear_fwd_f32(const float *Yin, int64_t ld_in, const float *
     cudaStream_t st = (cudaStream_t)stream;
     if (aligned16(Yin) && ld_in % 4 == 0 && ld_in >= (d_in + 3) / 4 * 4 && d_out <= 64) {      // 128-bit path
         dim3 grid((unsigned)cdiv(n, FBM), 1);
-        if (d_out <= 16) linear_fwd_tn_kernel<16><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
-        else if (d_out <= 32) linear_fwd_tn_kernel<32><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
-        else linear_fwd_tn_kernel<64><<<grid, F_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        if (d_out <= 16) linear_fwd_tn_kernel<16><<<grid, FW_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        else if (d_out <= 32) linear_fwd_tn_kernel<32><<<grid, FW_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
+        else linear_fwd_tn_kernel<64><<<grid, FW_THREADS, 0, st>>>(Yin, ld_in, W, b, H, ld_out, n, d_out, d_in, act);
         GAE_LAUNCH_CHECK();
         return GAE_OK;
     }
