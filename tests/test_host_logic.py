@@ -432,3 +432,28 @@ def test_halo_stage_tags_and_push_lists_host(lib_built):
     ex = _lib.HaloExchangeStruct()
     assert lib.gae_halo_push_f32(ctypes.byref(ex), 1, None) == -1
     assert lib.gae_halo_wait_f32(None, 0, 1, None) == -1
+
+
+def test_fp16_pair_split_scheme_of_the_tcgen05_decoder():
+    """The numeric scheme of csrc/decoder_tc16.cu restated in numpy (no GPU): operands scaled by the power of two that
+    puts max|z| in [2^13, 2^14), split into fp16 hi + fp16 lo, products hi*hi + lo*hi + hi*lo accumulated exactly --
+    the logits must come out within ~2^-21 of the fp64 product for embeddings of any magnitude; sigma's hi (truncated to
+    11 significand bits) + lo (fp16 of the remainder) must reproduce sigma to ~1e-7 absolute."""
+    rng = np.random.default_rng(0)
+    for scale in (1e-6, 1e-3, 1.0, 40.0, 3e4):
+        z = (rng.standard_normal((192, 16)) * scale).astype(np.float32)
+        sh = int(np.floor(np.log2(np.abs(z).max()))) - 13               # the kernel: exponent field - 127 - 13
+        zs = z * np.float32(2.0 ** -sh)
+        assert 2.0 ** 13 <= np.abs(zs).max() < 2.0 ** 14
+        hi = zs.astype(np.float16)
+        lo = (zs - hi.astype(np.float32)).astype(np.float16)
+        assert np.isfinite(hi.astype(np.float32)).all()
+        H, L = hi.astype(np.float64), lo.astype(np.float64)
+        S = (H @ H.T + L @ H.T + H @ L.T) * 4.0 ** sh
+        ref = z.astype(np.float64) @ z.astype(np.float64).T
+        assert np.abs(S - ref).max() / np.abs(ref).max() < 2e-6, scale
+    sg = (1.0 / (1.0 + np.exp(-rng.standard_normal(100000) * 6.0))).astype(np.float32)
+    hb = (sg.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = (sg - hb).astype(np.float16)
+    back = hb.astype(np.float16).astype(np.float64) + lo.astype(np.float64)
+    assert np.abs(back - sg.astype(np.float64)).max() < 1.5e-7
