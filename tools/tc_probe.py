@@ -37,7 +37,7 @@ def main():
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     # which tensor-core kernel: 1 = TF32 form (decoder_tc.cu), 2 = fp16-split pipelined form (decoder_tc16.cu)
-    TC = int(sys.argv[1]) if len(sys.argv) > 1 else _lib.get_tuning("dec_tc")
+    TC = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     _lib.set_tuning("dec_tc", TC)
     out, dump = {}, {}
     ok = True
