@@ -144,10 +144,11 @@ def load_graphs(args):
         from .synthetic import zinc_like_dataset
         print('Generating {} synthetic ZINC-shaped molecules'.format(args.synthetic))
         return zinc_like_dataset(args.synthetic, seed=args.seed or 0)
-    import dill
+    # train_inductive.py:79-81 reads the list with dill.load, which needs the DGL build that wrote it;
+    # dgl_pickle reads the same file without DGL (graphs of this package pass through unchanged)
+    from .dgl_pickle import load_graph_list
     print('Loading data')
-    with open(args.data_file, 'rb') as f:
-        return dill.load(f)
+    return load_graph_list(args.data_file)
 
 
 def plot(train_losses, val_losses, save_dir):
