@@ -228,3 +228,22 @@ def test_train_inductive_loads_a_dgl_written_file(tmp_path):
     args = TI.build_parser().parse_args(["--data_file", path])
     graphs = TI.load_graphs(args)
     assert len(graphs) == len(SPECS) and all(isinstance(g, G.DGLGraph) for g in graphs)
+
+
+@pytest.mark.gpu
+def test_dgl_written_file_trains_on_the_gpu(cuda, tmp_path):
+    """train_inductive.py:79-81 -> :34 -> :43-53 over a DGL-written file: the graphs read without DGL are
+    collated on the device and one step matches the fp64 oracle (1e-5, the bar of tests/test_parity_gpu.py)."""
+    from oracle import gae_oracle as O
+    from tests.test_parity_gpu import _check_step
+    graphs = dgl_pickle.load_graph_list(write_with_lookalike(tmp_path, "0.4"))
+    bg = G.batch(graphs, device=cuda)
+    s, d, n = O.batch_graphs([(*g.edges(), g.number_of_nodes()) for g in graphs])
+    rp, col = O.coo_to_csr(s, d, n)
+    assert torch.equal(bg.csr().rowptr.cpu(), rp) and torch.equal(bg.csr().col.cpu(), col)      # bit-exact indexing
+    X = bg.ndata["h"].cpu() / 40.0
+    torch.manual_seed(3)
+    ref = O.OracleGAE(39, [32, 16])
+    weights = [(l.apply_mod.linear.weight.detach(), l.apply_mod.linear.bias.detach()) for l in ref.layers]
+    mask = torch.rand(n, 16) >= 0.1
+    _check_step(cuda, bg, X, weights, mask)

@@ -453,6 +453,35 @@ def test_train_step_parity_zinc_batch(cuda, batch_size):
     _check_step(cuda, bg, X, weights, mask)
 
 
+def _degenerate_graph(kind):
+    """Edge cases of the graph side of the step (the domain's empty / ragged / collision inputs)."""
+    if kind == "two_nodes_one_self_loop":      # the smallest graph with a non-trivial loss (n = 1 gives pos_weight 0)
+        return [0], [0], 2
+    if kind == "isolated_dups_loops":          # isolated nodes, a triple edge, self loops, an empty last row
+        return [0, 0, 0, 1, 2, 2, 4], [1, 1, 1, 0, 2, 3, 4], 7
+    if kind == "star_in_129":                  # every node points at node 5 (one long row), n crosses a 128-row tile
+        return list(range(129)) + [5, 5], [5] * 129 + [9, 9], 129
+    if kind == "path_directed_300":            # directed, A != A^T: exercises CSR(A) vs CSR(A^T) orientation
+        return list(range(299)), list(range(1, 300)), 300
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["two_nodes_one_self_loop", "isolated_dups_loops", "star_in_129", "path_directed_300"])
+@pytest.mark.parametrize("hidden", [[16], [24, 20, 8]])
+def test_train_step_parity_degenerate_graphs(cuda, kind, hidden):
+    """One full step (gae.py:49-55 + train_inductive.py:44-52) on degenerate graphs, one- and three-layer
+    encoders (gae.py:36-45: a single layer carries the identity), embedding widths 16 and 8."""
+    src, dst, n = _degenerate_graph(kind)
+    g = G.DGLGraph((np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), n))
+    gen = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 11, generator=gen)
+    torch.manual_seed(n + len(hidden))
+    ref = O.OracleGAE(11, hidden)
+    weights = [(l.apply_mod.linear.weight.detach(), l.apply_mod.linear.bias.detach()) for l in ref.layers]
+    mask = torch.rand(n, hidden[-1], generator=gen) >= 0.1
+    _check_step(cuda, g, X, weights, mask)
+
+
 def test_dense_reference_formulation_matches_fused(cuda):
     """train_inductive.py:44-48 executed literally (dense adj, forward(g), torch BCE) gives the
     same loss and gradients as the fused path."""
