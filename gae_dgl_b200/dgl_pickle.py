@@ -30,7 +30,7 @@ from __future__ import annotations
 
 import io
 import pickle
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Tuple
 
 import numpy as np
 import torch
